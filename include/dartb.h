@@ -1,0 +1,172 @@
+/*
+ * dartb.h — C-ABI of the B200-native batched DART stepper (libdartb.so).
+ *
+ * This is the drop-in boundary for the pydart2 calls made by the reference's
+ * gym/envs/dart/dart_env.py.  Every entry point names the reference
+ * call site it replaces.  Plain C types only: no torch, no C++ in the signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dartb_last_error()
+ *     returns a thread-local message for the last failure.  No exception crosses the ABI.
+ *   - `d_*` pointers are DEVICE pointers owned by the caller (e.g. torch tensors);
+ *     `h_*` pointers are HOST pointers.  Nothing is retained past the call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ *     work is enqueued on it; no hidden synchronisation except in the h_* calls.
+ *   - boundary arrays are row-major [n_worlds, k] float32 (north_star: "fp32").
+ *     Internally state is SoA [k][n_worlds].
+ *   - a handle is bound to one device and used from one host thread at a time.
+ *   - there is NO CPU fallback: without a CUDA device dartb_create fails.
+ */
+#ifndef DARTB_H
+#define DARTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DARTB_MAX_BODIES 24
+#define DARTB_MAX_SHAPES 24
+#define DARTB_MAX_GROUND 4
+#define DARTB_MAX_ACT 16
+
+enum { DARTB_JOINT_WELD = 0, DARTB_JOINT_REVOLUTE = 1, DARTB_JOINT_PRISMATIC = 2 };
+enum { DARTB_SHAPE_BOX = 0, DARTB_SHAPE_CAPSULE = 1, DARTB_SHAPE_SPHERE = 2,
+       DARTB_SHAPE_ELLIPSOID = 3, DARTB_SHAPE_CYLINDER = 4 };
+
+/* One BodyNode + its parent Joint (DART creates them as a pair).  Filled by the host
+ * model compiler (dart_env_b200/skel.py) which restates DART's SkelParser; replaces
+ * pydart.World(dt, skel_path) at dart_env.py:54-55. */
+typedef struct dartb_body {
+    int32_t parent;            /* -1 = world */
+    int32_t joint_type;        /* DARTB_JOINT_* */
+    int32_t dof;               /* index into q, -1 for weld */
+    int32_t limit_enforced;    /* dart_env.py:64-67 */
+    double  T_parent_joint[12];/* 3x4 row-major [R|p]: joint frame in the parent body frame */
+    double  T_child_joint[12]; /* joint frame in the child body frame */
+    double  axis[3];           /* joint axis in the joint frame (unit) */
+    double  q_lo, q_hi;
+    double  damping, coulomb, spring_k, spring_rest;
+    double  q_init, dq_init;
+    double  mass;
+    double  com[3];            /* local COM */
+    double  inertia[9];        /* moment about the COM, body axes, row-major */
+    double  friction_coeff;    /* BodyNode friction, default 1.0 */
+} dartb_body_t;
+
+typedef struct dartb_shape {
+    int32_t body;              /* robot body index; -1 = world-fixed */
+    int32_t type;              /* DARTB_SHAPE_* */
+    double  size[3];           /* box xyz | capsule (radius,height,-) | sphere (r,-,-) */
+    double  T[12];             /* 3x4 row-major, body-local (or world for body = -1) */
+} dartb_shape_t;
+
+typedef struct dartb_model {
+    double  dt;
+    double  gravity[3];
+    int32_t n_bodies, n_dofs, n_shapes, n_ground;
+    dartb_body_t  bodies[DARTB_MAX_BODIES];
+    dartb_shape_t shapes[DARTB_MAX_SHAPES];
+    dartb_shape_t ground[DARTB_MAX_GROUND];
+} dartb_model_t;
+
+/* Task layer: the arithmetic in gym/envs/dart/{hopper,walker2d,half_cheetah,snake_7link}.py
+ * step()/advance()/_get_obs()/reset_model(), parameterised. */
+enum { DARTB_OBS_Q1_DQ = 0,       /* [q[1:], dq]                 half_cheetah.py:79-85, snake_7link.py:89-99 */
+       DARTB_OBS_HEIGHT_Q2_DQ = 1 /* [com_y(body), q[2:], clip(dq)] hopper.py:67-74, walker2d.py:67-74 */ };
+
+typedef struct dartb_task {
+    int32_t frame_skip;            /* dart_env.py:170 n_frames */
+    int32_t n_act, n_obs;
+    int32_t act_dof[DARTB_MAX_ACT];/* tau[act_dof[i]] = clamp(a[i], lo, hi) * scale[i] */
+    double  act_scale[DARTB_MAX_ACT];
+    double  act_lo[DARTB_MAX_ACT], act_hi[DARTB_MAX_ACT];
+    int32_t obs_mode;              /* DARTB_OBS_* */
+    double  dq_clip;               /* > 0: clip dq in obs to +-dq_clip (hopper.py:70), 0: none */
+    int32_t height_body;           /* bodynodes[i].com()[1] (hopper.py:42); -1: unused */
+    double  height_lo, height_hi;  /* done unless lo < height < hi; +-inf disables */
+    double  ang_max;               /* done unless |q[2]| < ang_max */
+    double  alive_bonus;
+    double  ctrl_cost;             /* reward -= ctrl_cost * sum(a^2) with the RAW action */
+    double  vel_weight;
+    int32_t limit_pen_dof;         /* hopper.py:45-50 joint-limit penalty dof, -1: none */
+    double  limit_pen_margin, limit_pen_weight;
+    double  dev_cost;              /* snake_7link.py:80: reward -= dev_cost * |q[2]| */
+    int32_t zero_reward_on_blowup; /* half_cheetah.py:55-59 */
+    int32_t fluid_force;           /* snake_7link.py:35-50 per-substep fluid force */
+    double  fluid_offset, fluid_coef; /* 0.05, 50.0 */
+    double  reset_noise;           /* U(-noise, +noise) on q and dq (hopper.py:78-79) */
+    double  state_bound;           /* 100: done if any |s[2:]| >= bound or non-finite */
+} dartb_task_t;
+
+/* Options for dartb_set_option */
+enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
+       DARTB_OPT_PGS_ITERS = 2,
+       DARTB_OPT_FRICTION_ALL = 3 /* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */ };
+
+typedef struct dartb_engine* dartb_handle_t;
+
+/* Build an engine stepping n_worlds copies of `model` on CUDA device `device`.
+ * `world_offset` is the global id of this handle's first world (RNG streams are keyed by
+ * global world id so results do not depend on how worlds are sharded across GPUs).
+ * Replaces pydart.init() + DartWorld(dt, path) (dart_env.py:19,54-59). */
+int dartb_create(const dartb_model_t* model, const dartb_task_t* task, int32_t n_worlds,
+                 int32_t device, uint64_t seed, int64_t world_offset, dartb_handle_t* out);
+int dartb_destroy(dartb_handle_t h);
+
+int dartb_set_option(dartb_handle_t h, int32_t key, double value);
+
+/* world.reset() + reset_model(): q0 + U(+-noise), dq0 + U(+-noise), returns obs.
+ * d_mask: uint8[n] (NULL = all worlds). d_obs may be NULL.  (dart_world.py:20-22, hopper.py:76-84) */
+int dartb_reset(dartb_handle_t h, const uint8_t* d_mask, float* d_obs, void* stream);
+
+/* set_positions/set_velocities and q/dq reads (dart_env.py:145-148, 211-215). [n, nd] fp32. */
+int dartb_set_state(dartb_handle_t h, const float* d_q, const float* d_dq, void* stream);
+int dartb_get_state(dartb_handle_t h, float* d_q, float* d_dq, void* stream);
+/* fp64 variants used by the tight-tolerance parity tests (engine created with fp64 state). */
+int dartb_set_state_f64(dartb_handle_t h, const double* d_q, const double* d_dq, void* stream);
+int dartb_get_state_f64(dartb_handle_t h, double* d_q, double* d_dq, void* stream);
+
+/* One env.step(): clamp/scale action, frame_skip x {set_forces; world.step()}, obs/reward/done,
+ * optional auto-reset of done worlds (gym/vector/sync_vector_env.py:76-79 semantics: the returned
+ * obs of a done world is its reset obs).  d_action [n,n_act], d_obs [n,n_obs], d_reward [n],
+ * d_done uint8[n].  (hopper.py:24-65 and siblings; dart_env.py:158-175) */
+int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_reward,
+               uint8_t* d_done, int32_t auto_reset, void* stream);
+
+/* Exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175): one DART time step
+ * with generalized forces d_tau [n, nd]; optional external world-frame forces at body
+ * origins d_fext [n, n_bodies, 3] (bn.add_ext_force, snake_7link.py:47), may be NULL. */
+int dartb_substep(dartb_handle_t h, const float* d_tau, const float* d_fext, void* stream);
+int dartb_substep_f64(dartb_handle_t h, const double* d_tau, const double* d_fext, void* stream);
+
+/* world.collision_result.contacts of the LAST sub-step (walker2d.py:38-41).
+ * d_count int32[n]; d_body int32[n, max_contacts] (robot body index per contact, -1 padded,
+ * ordered by collision-shape index); d_data float[n, max_contacts, 10] =
+ * point(3) normal(3) depth(1) force(3).  Any pointer may be NULL. */
+int dartb_get_contacts(dartb_handle_t h, int32_t* d_count, int32_t* d_body, float* d_data,
+                       void* stream);
+int32_t dartb_max_contacts(dartb_handle_t h);
+
+/* Introspection used by the host wrapper and the tests */
+int32_t dartb_num_worlds(dartb_handle_t h);
+int32_t dartb_num_dofs(dartb_handle_t h);
+int32_t dartb_is_f64(dartb_handle_t h);
+/* number of CUDA kernels this handle has launched since creation (bench gpu_launches) */
+int64_t dartb_launch_count(dartb_handle_t h);
+/* Which kernel specialisation the model was lowered to, e.g. "planar-xy/static:hopper6" */
+const char* dartb_kernel_name(dartb_handle_t h);
+
+/* Engines created with this flag set keep fp64 state and run the fp64 instantiation of the
+ * kernels (validation path: separates algorithmic from precision differences). */
+int dartb_create_f64(const dartb_model_t* model, const dartb_task_t* task, int32_t n_worlds,
+                     int32_t device, uint64_t seed, int64_t world_offset, dartb_handle_t* out);
+
+const char* dartb_last_error(void);
+const char* dartb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DARTB_H */
