@@ -23,7 +23,7 @@
  *     collision_result.contacts[*].force                        walker2d.py:38-41
  *     set_position_limit_enforced  dart_env.py:64-67
  * The task layer (obs / reward / done / reset) restates hopper.py:24-84, walker2d.py:22-82,
- * half_cheetah.py:27-101, snake_7link.py:35-122 and IS pinned: tests/golden/*.npz are produced
+ * half_cheetah.py:27-101, snake_7link.py:35-122 and IS pinned: tests/golden/ npz files are produced
  * by running those reference classes unmodified on top of this physics (oracle/pydart2_shim).
  *
  * Step semantics (DART World::step, Appendix B.3):
@@ -229,6 +229,8 @@ typedef struct orc_world {
     double lcpA[MAXROWS * MAXROWS], lcpx[MAXROWS], lcpb[MAXROWS], lcplo[MAXROWS], lcphi[MAXROWS];
     int lcpfindex[MAXROWS];
     int limit_active[NB];        /* per dof: 0 none, -1 lower, +1 upper (last step) */
+    double shape_gap[MAXC];      /* per robot shape: min over statics of (distance - radius) */
+    double shape_tilt[MAXC];     /* per robot shape: |height difference of the capsule ends| */
     /* options */
     int lcp_mode;                /* 0 dantzig, 1 pgs */
     int pgs_iters;
@@ -530,6 +532,8 @@ static void collide(orc_world_t* w) {
         xf_t Tl, Ts;
         xf_from12(sh->T, &Tl);
         xf_mul(&w->Tw[sh->body], &Tl, &Ts);
+        w->shape_gap[si] = INFINITY;
+        w->shape_tilt[si] = INFINITY;
         for (int gi = 0; gi < w->m.n_ground; gi++) {
             const dartb_shape_t* g = &w->m.ground[gi];
             if (g->type != DARTB_SHAPE_BOX) continue; /* only box statics collide (in scope) */
@@ -542,11 +546,19 @@ static void collide(orc_world_t* w) {
                 for (int k = 0; k < 3; k++) { p1[k] = Ts.p[k] + hl * ax[k]; p2[k] = Ts.p[k] - hl * ax[k]; }
                 closest_segment_box(p1, p2, Tg.p, Tg.R, g->size, pl, pb);
                 radius = sh->size[0];
+                double up[3] = {Tg.R[1], Tg.R[4], Tg.R[7]}, dd[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+                double tilt = fabs(v3dot(up, dd));
+                if (tilt < w->shape_tilt[si]) w->shape_tilt[si] = tilt;
             } else if (sh->type == DARTB_SHAPE_SPHERE) {
                 closest_segment_box(Ts.p, Ts.p, Tg.p, Tg.R, g->size, pl, pb);
                 radius = sh->size[0];
             } else {
                 continue; /* box / ellipsoid robot shapes: out of scope */
+            }
+            {
+                double dv[3] = {pl[0] - pb[0], pl[1] - pb[1], pl[2] - pb[2]};
+                double gap = sqrt(v3dot(dv, dv)) - radius;
+                if (gap < w->shape_gap[si]) w->shape_gap[si] = gap;
             }
             if (w->ncontacts >= MAXC) continue;
             contact_t* c = &w->contacts[w->ncontacts];
@@ -909,6 +921,8 @@ void orc_get_contact(const orc_world_t* w, int i, int* body, double* point, doub
     *depth = c->depth;
     for (int k = 0; k < 3; k++) { point[k] = c->point[k]; normal[k] = c->normal[k]; force[k] = c->force[k]; }
 }
+double orc_shape_gap(const orc_world_t* w, int si) { return w->shape_gap[si]; }
+double orc_shape_tilt(const orc_world_t* w, int si) { return w->shape_tilt[si]; }
 int orc_limit_active(const orc_world_t* w, int dof) { return w->limit_active[dof]; }
 int orc_lcp_rows(const orc_world_t* w) { return w->nrows; }
 void orc_get_lcp(const orc_world_t* w, double* A, double* x, double* b, double* lo, double* hi, int* findex) {

@@ -45,7 +45,7 @@ def lib():
             "orc_body_transform": (None, [P, I, dp]), "orc_body_com": (None, [P, I, dp]),
             "orc_body_com_spatial_velocity": (None, [P, I, dp]), "orc_add_ext_force": (None, [P, I, dp]),
             "orc_num_contacts": (I, [P]), "orc_get_contact": (None, [P, I, ip, dp, dp, dp, dp]),
-            "orc_limit_active": (I, [P, I]), "orc_lcp_rows": (I, [P]),
+            "orc_limit_active": (I, [P, I]), "orc_shape_gap": (D, [P, I]), "orc_shape_tilt": (D, [P, I]), "orc_lcp_rows": (I, [P]),
             "orc_get_lcp": (None, [P, dp, dp, dp, dp, dp, ip]), "orc_lcp_failed": (I, [P]),
             "orc_mass_matrix": (None, [P, dp]), "orc_forward_dynamics": (None, [P, dp]),
             "orc_energy": (D, [P]),
@@ -150,6 +150,12 @@ class OracleWorld:
             self._L.orc_get_contact(self._h, i, C.byref(body), _dp(p), _dp(n), C.byref(depth), _dp(f))
             out.append(dict(body=body.value, point=p, normal=n, depth=depth.value, force=f))
         return out
+
+    def shape_gaps(self):
+        """per robot shape: (distance - radius) to the nearest static, and capsule end-height difference"""
+        n = len(self.model.shapes)
+        return (np.array([self._L.orc_shape_gap(self._h, i) for i in range(n)]),
+                np.array([self._L.orc_shape_tilt(self._h, i) for i in range(n)]))
 
     def limit_active(self):
         return np.array([self._L.orc_limit_active(self._h, d) for d in range(self.nd)])

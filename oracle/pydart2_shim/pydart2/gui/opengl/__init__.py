@@ -1,0 +1,1 @@
+"""Stub: lets the unmodified reference env modules import without GL (test infrastructure)."""
