@@ -1,0 +1,672 @@
+// planar_kernels.cuh — hand-written sm_100a device code for one DART time step of a planar
+// skeleton, one world per thread, the whole world state in registers.
+//
+// What it computes is DART's World::step as restated by oracle/dart_oracle.c:
+//   K1 forward kinematics            (BodyNode::updateTransform/updateVelocity/updatePartialAcceleration)
+//   K2 ABA backward pass             (updateArtInertia [implicit damping/spring] + updateBiasForce)
+//   K3 ABA forward pass + dq += dt*ddq  (updateAccelerationFD, integrateVelocities)
+//   K4 capsule vs static box         (ODE dCollideCapsuleBox: dClosestLineBoxPoints + sphere/point)
+//   K5 contact + joint-limit rows, A = J M^-1 J^T (+CFM) by impulse passes with the PLAIN
+//      articulated inertia (ContactConstraint / JointLimitConstraint / applyUnitImpulse)
+//   K6 boxed LCP: Dantzig pivoting with ODE's two-stage friction bounds, or fixed-sweep PGS
+//   K7 dq += M^-1 J^T x ; q += dt*dq  (computeImpulseForwardDynamics, integratePositions)
+// replacing the pydart2 call at gym/envs/dart/dart_env.py:174-175 of the reference.
+//
+// Layout: the skeleton TOPOLOGY (parents, joint types, shape->body map) is a compile-time
+// policy `T`, so every per-body loop is unrolled and per-body quantities live in registers;
+// the PARAMETERS (masses, anchors, limits...) are a __grid_constant__ kernel argument, i.e.
+// constant-bank operands.  Spatial vectors are planar 3-vectors [angular; lin_x; lin_y] in
+// WORLD axes taken at each body's own origin, so parent<->child transforms are pure shifts.
+// Only the LCP (variable row count) uses thread-local memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "planar_model.h"
+
+#define DEVI __device__ __forceinline__
+
+// ------------------------------------------------------------------------ static loops
+template <int I, int N, class F>
+DEVI void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+template <int I, class F>
+DEVI void static_rfor(F&& f) {  // I-1, ..., 0
+    if constexpr (I > 0) {
+        f(std::integral_constant<int, I - 1>{});
+        static_rfor<I - 1>(f);
+    }
+}
+
+// ------------------------------------------------------------------------ topologies
+// (after the weld merge of lower.h; signature strings must match lower_model()'s)
+template <int NB_, int NS_, int NL_>
+struct TopoBase {
+    static constexpr int NB = NB_, NS = NS_, NL = NL_;
+    static constexpr int NSA = NS_ > 0 ? NS_ : 1;
+    static constexpr int NR = 2 * NS_ + NL_;  // max LCP rows: (normal, tangent) per capsule + limits
+};
+struct TopoHopper : TopoBase<6, 4, 3> {  // hopper_capsule.skel: x, y, rot, thigh, shin, foot
+    static constexpr const char* name = "hopper6";
+    static constexpr const char* sig = "P-1,P0,R1,R2,R3,R4,S2,S3,S4,S5,";
+    __host__ __device__ static constexpr int parent(int i) { constexpr int p[NB] = {-1, 0, 1, 2, 3, 4}; return p[i]; }
+    __host__ __device__ static constexpr int jtype(int i) { constexpr int t[NB] = {2, 2, 1, 1, 1, 1}; return t[i]; }
+    __host__ __device__ static constexpr int sbody(int s) { constexpr int b[NSA] = {2, 3, 4, 5}; return b[s]; }
+};
+struct TopoWalker : TopoBase<9, 7, 6> {  // walker2d.skel: root(3) + two 3-link legs
+    static constexpr const char* name = "walker9";
+    static constexpr const char* sig = "P-1,P0,R1,R2,R3,R4,R2,R6,R7,S2,S3,S4,S5,S6,S7,S8,";
+    __host__ __device__ static constexpr int parent(int i) { constexpr int p[NB] = {-1, 0, 1, 2, 3, 4, 2, 6, 7}; return p[i]; }
+    __host__ __device__ static constexpr int jtype(int i) { constexpr int t[NB] = {2, 2, 1, 1, 1, 1, 1, 1, 1}; return t[i]; }
+    __host__ __device__ static constexpr int sbody(int s) { constexpr int b[NSA] = {2, 3, 4, 5, 6, 7, 8}; return b[s]; }
+};
+struct TopoCheetah : TopoBase<9, 8, 6> {  // half_cheetah.skel, head welded into the torso
+    static constexpr const char* name = "cheetah9";
+    static constexpr const char* sig = "P-1,P0,R1,R2,R3,R4,R2,R6,R7,S2,S2,S3,S4,S5,S6,S7,S8,";
+    __host__ __device__ static constexpr int parent(int i) { constexpr int p[NB] = {-1, 0, 1, 2, 3, 4, 2, 6, 7}; return p[i]; }
+    __host__ __device__ static constexpr int jtype(int i) { constexpr int t[NB] = {2, 2, 1, 1, 1, 1, 1, 1, 1}; return t[i]; }
+    __host__ __device__ static constexpr int sbody(int s) { constexpr int b[NSA] = {2, 2, 3, 4, 5, 6, 7, 8}; return b[s]; }
+};
+struct TopoSnake : TopoBase<9, 0, 6> {  // snake_7link.skel: 9-chain, never touches the ground
+    static constexpr const char* name = "snake9";
+    static constexpr const char* sig = "P-1,P0,R1,R2,R3,R4,R5,R6,R7,";
+    __host__ __device__ static constexpr int parent(int i) { constexpr int p[NB] = {-1, 0, 1, 2, 3, 4, 5, 6, 7}; return p[i]; }
+    __host__ __device__ static constexpr int jtype(int i) { constexpr int t[NB] = {2, 2, 1, 1, 1, 1, 1, 1, 1}; return t[i]; }
+    __host__ __device__ static constexpr int sbody(int) { return 0; }
+};
+
+template <class T>
+__host__ __device__ constexpr bool topo_has_child(int i) {
+    for (int k = 0; k < T::NB; k++) if (T::parent(k) == i) return true;
+    return false;
+}
+template <class T>
+__host__ __device__ constexpr bool topo_is_ancestor(int j, int b) {  // j == b or j above b
+    for (int k = b; k >= 0; k = T::parent(k)) if (k == j) return true;
+    return false;
+}
+
+// ------------------------------------------------------------------------ scalar helpers
+template <typename R> struct Num;
+template <> struct Num<float> {
+    static DEVI void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+    static DEVI float sqrt_(float x) { return sqrtf(x); }
+    static DEVI float abs_(float x) { return fabsf(x); }
+    static DEVI float inf() { return __int_as_float(0x7f800000); }
+    static DEVI float inert() { return 1e-14f; }
+};
+template <> struct Num<double> {
+    static DEVI void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+    static DEVI double sqrt_(double x) { return sqrt(x); }
+    static DEVI double abs_(double x) { return fabs(x); }
+    static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static DEVI double inert() { return 1e-14; }
+};
+
+// DART constants (ContactConstraint.cpp / JointLimitConstraint.cpp), see oracle/dart_oracle.c
+#define DK_CONTACT_ERP 0.01
+#define DK_CONTACT_MAX_ERV 1e-3
+#define DK_CONTACT_CFM 1e-5
+#define DK_LIMIT_CFM 1e-9
+#define DK_FRICTION_THRESHOLD 1e-3
+#define DK_CONTACT_EPS 1e-6
+
+// ------------------------------------------------------------------------ Philox4x32-10
+// identical to oracle/dart_oracle.c::orc_reset_uniform so reset noise is bit-identical
+DEVI void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = h1 ^ c[1] ^ k0, n1 = l1, n2 = h0 ^ c[3] ^ k1, n3 = l0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+DEVI float reset_uniform(uint64_t seed, int64_t world, uint32_t episode, int i) {
+    uint32_t c[4] = {(uint32_t)world, (uint32_t)((uint64_t)world >> 32), episode, (uint32_t)(i >> 2)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t bits = c[i & 3];
+    float u = __fmul_rn((float)(bits >> 8), 1.0f / 16777216.0f);
+    return __fadd_rn(__fmul_rn(u, 2.0f), -1.0f);
+}
+
+// ------------------------------------------------------------------------ K4: segment vs box (2-D)
+// ODE dClosestLineBoxPoints restricted to the plane (the out-of-plane axis has v = 0, region 0).
+// Exact minimiser of the convex piecewise-quadratic distance along p1->p2; ties -> t = 0 (p1).
+template <typename R>
+DEVI void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R hy, R& lx, R& ly, R& bx, R& by) {
+    R s[2] = {p1x - cx, p1y - cy}, v[2] = {p2x - p1x, p2y - p1y}, sg[2], v2[2], ta[2];
+    const R h[2] = {hx, hy};
+    const R dvx = v[0], dvy = v[1];
+    int reg[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (v[i] < 0) { s[i] = -s[i]; v[i] = -v[i]; sg[i] = (R)-1; } else sg[i] = (R)1;
+        v2[i] = v[i] * v[i];
+        if (v[i] > (R)1e-19) {
+            if (s[i] < -h[i]) { reg[i] = -1; ta[i] = (-h[i] - s[i]) / v[i]; }
+            else { reg[i] = (s[i] > h[i]) ? 1 : 0; ta[i] = (h[i] - s[i]) / v[i]; }
+        } else { reg[i] = 0; ta[i] = (R)2; }
+    }
+    R t = 0, dd = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) dd -= (reg[i] ? v2[i] : (R)0) * ta[i];
+    if (dd < 0) {
+        bool found = false;
+        for (int it = 0; it < 8; it++) {
+            R nt = 1;
+#pragma unroll
+            for (int i = 0; i < 2; i++) if (ta[i] > t && ta[i] < (R)1 && ta[i] < nt) nt = ta[i];
+            R nd = 0;
+#pragma unroll
+            for (int i = 0; i < 2; i++) nd += (reg[i] ? v2[i] : (R)0) * (nt - ta[i]);
+            if (nd >= 0) {
+                R mm = (nd - dd) / (nt - t);
+                t -= dd / mm;
+                found = true;
+                break;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) if (ta[i] == nt) { ta[i] = (h[i] - s[i]) / v[i]; reg[i]++; }
+            t = nt;
+            dd = nd;
+            if (!(t < (R)1)) break;
+        }
+        if (!found) t = 1;
+    }
+    lx = p1x + t * dvx;
+    ly = p1y + t * dvy;
+    R q0 = sg[0] * (s[0] + t * v[0]), q1 = sg[1] * (s[1] + t * v[1]);
+    q0 = q0 < -hx ? -hx : (q0 > hx ? hx : q0);
+    q1 = q1 < -hy ? -hy : (q1 > hy ? hy : q1);
+    bx = q0 + cx;
+    by = q1 + cy;
+}
+
+// ------------------------------------------------------------------------ K6: boxed LCP
+// Dense Cholesky solve of the nC x nC system A[idx,idx] y = rhs (thread-local scratch L).
+template <typename R, int NR>
+DEVI bool chol_solve_sub(int n, const R* A, const int* idx, int nC, const R* rhs, R* y, R* L) {
+    for (int a = 0; a < nC; a++) {
+        const int ia = idx[a];
+        for (int b = 0; b <= a; b++) {
+            R s = A[ia * n + idx[b]];
+            for (int k = 0; k < b; k++) s -= L[a * NR + k] * L[b * NR + k];
+            if (a == b) {
+                if (!(s > 0)) return false;
+                L[a * NR + a] = Num<R>::sqrt_(s);
+            } else L[a * NR + b] = s / L[b * NR + b];
+        }
+    }
+    for (int a = 0; a < nC; a++) {
+        R s = rhs[a];
+        for (int k = 0; k < a; k++) s -= L[a * NR + k] * y[k];
+        y[a] = s / L[a * NR + a];
+    }
+    for (int a = nC - 1; a >= 0; a--) {
+        R s = y[a];
+        for (int k = a + 1; k < nC; k++) s -= L[k * NR + a] * y[k];
+        y[a] = s / L[a * NR + a];
+    }
+    return true;
+}
+
+// ODE dSolveLCP (Dantzig driving-index loop) as restated in oracle/dart_oracle.c:
+// non-friction rows first; when the first friction row is reached its bounds become
+// +-|mu * x[findex]| from the frictionless normal impulses and stay fixed.
+template <typename R, int NR>
+DEVI void lcp_dantzig(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int* fidx) {
+    R w[NR], dx[NR], dw[NR], L[NR * NR], rhs[NR], sol[NR];
+    int idx[NR];
+    uint32_t inC = 0, inN = 0, st = 0;
+    for (int i = 0; i < n; i++) { x[i] = 0; w[i] = 0; }
+    const R INF = Num<R>::inf();
+    bool failed = false;
+    for (int phase = 0; phase < 2 && !failed; phase++) {
+        if (phase == 1) {
+            bool any = false;
+            for (int k = 0; k < n; k++)
+                if (fidx[k] >= 0) {
+                    any = true;
+                    R wfk = x[fidx[k]];
+                    if (wfk == 0) { hi[k] = 0; lo[k] = 0; }
+                    else { hi[k] = Num<R>::abs_(hi[k] * wfk); lo[k] = -hi[k]; }
+                }
+            if (!any) break;
+        }
+        for (int i = 0; i < n && !failed; i++) {
+            if ((fidx[i] >= 0) != (phase == 1)) continue;
+            const uint32_t bi = 1u << i;
+            if (!(A[i * n + i] > Num<R>::inert())) { x[i] = 0; w[i] = 0; lo[i] = 0; hi[i] = 0; inN |= bi; continue; }
+            R wi = -b[i];
+            const uint32_t live = inC | inN;
+            for (int j = 0; j < n; j++) if (live >> j & 1) wi += A[i * n + j] * x[j];
+            w[i] = wi;
+            if (lo[i] == 0 && wi >= 0) { inN |= bi; st &= ~bi; continue; }
+            if (hi[i] == 0 && wi <= 0) { inN |= bi; st |= bi; continue; }
+            if (wi == 0) { inC |= bi; continue; }
+            bool placed = false;
+            for (int guard = 0; guard < 10 * n + 50; guard++) {
+                const R dirf = (w[i] <= 0) ? (R)1 : (R)-1;
+                int nC = 0;
+                for (int j = 0; j < n; j++) if (inC >> j & 1) idx[nC++] = j;
+                for (int r = 0; r < nC; r++) rhs[r] = -dirf * A[idx[r] * n + i];
+                if (nC > 0 && !chol_solve_sub<R, NR>(n, A, idx, nC, rhs, sol, L)) { failed = true; break; }
+                for (int r = 0; r < nC; r++) dx[idx[r]] = sol[r];
+                for (int j = 0; j < n; j++) {
+                    if (!((inN >> j & 1) || j == i)) continue;
+                    R s = A[j * n + i] * dirf;
+                    for (int r = 0; r < nC; r++) s += A[j * n + idx[r]] * sol[r];
+                    dw[j] = s;
+                }
+                int cmd = 1, si = 0;
+                R s = -w[i] / dw[i];
+                if (dirf > 0) {
+                    if (hi[i] < INF) { R s2 = (hi[i] - x[i]) * dirf; if (s2 < s) { s = s2; cmd = 3; } }
+                } else {
+                    if (lo[i] > -INF) { R s2 = (lo[i] - x[i]) * dirf; if (s2 < s) { s = s2; cmd = 2; } }
+                }
+                for (int k = 0; k < n; k++) {
+                    if (!(inN >> k & 1)) continue;
+                    const bool stk = st >> k & 1;
+                    if ((!stk && dw[k] < 0) || (stk && dw[k] > 0)) {
+                        if (lo[k] == 0 && hi[k] == 0) continue;
+                        R s2 = -w[k] / dw[k];
+                        if (s2 < s) { s = s2; cmd = 4; si = k; }
+                    }
+                }
+                for (int r = 0; r < nC; r++) {
+                    const int k = idx[r];
+                    if (sol[r] < 0 && lo[k] > -INF) { R s2 = (lo[k] - x[k]) / sol[r]; if (s2 < s) { s = s2; cmd = 5; si = k; } }
+                    if (sol[r] > 0 && hi[k] < INF) { R s2 = (hi[k] - x[k]) / sol[r]; if (s2 < s) { s = s2; cmd = 6; si = k; } }
+                }
+                if (!(s > 0)) {
+                    if (s != s) { failed = true; break; }
+                    s = 0;  // rounding produced a tiny negative step: take a zero step and switch
+                }
+                for (int r = 0; r < nC; r++) x[idx[r]] += s * sol[r];
+                x[i] += s * dirf;
+                for (int k = 0; k < n; k++) if (inN >> k & 1) w[k] += s * dw[k];
+                w[i] += s * dw[i];
+                const uint32_t bs = 1u << si;
+                switch (cmd) {
+                    case 1: w[i] = 0; inC |= bi; break;
+                    case 2: x[i] = lo[i]; st &= ~bi; inN |= bi; break;
+                    case 3: x[i] = hi[i]; st |= bi; inN |= bi; break;
+                    case 4: w[si] = 0; inN &= ~bs; inC |= bs; break;
+                    case 5: x[si] = lo[si]; st &= ~bs; inC &= ~bs; inN |= bs; break;
+                    default: x[si] = hi[si]; st |= bs; inC &= ~bs; inN |= bs; break;
+                }
+                if (cmd <= 3) { placed = true; break; }
+            }
+            if (!placed && !failed) { inN |= bi; }
+        }
+    }
+    if (failed) {  // ODE: "LCP internal error": keep what was solved, finite values only
+        for (int i = 0; i < n; i++) if (!(x[i] == x[i]) || Num<R>::abs_(x[i]) == INF) x[i] = 0;
+    }
+}
+
+// fixed-sweep PGS (oracle/dart_oracle.c::orc_solve_lcp_pgs; DART PGSLCPSolver shape)
+template <typename R>
+DEVI void lcp_pgs(int n, const R* A, R* x, const R* b, const R* lo, const R* hi, const int* fidx, int iters) {
+    for (int i = 0; i < n; i++) x[i] = 0;
+    for (int it = 0; it < iters; it++)
+        for (int i = 0; i < n; i++) {
+            const R aii = A[i * n + i];
+            if (aii < (R)1e-9) { x[i] = 0; continue; }
+            R s = b[i];
+            for (int j = 0; j < n; j++) if (j != i) s -= A[i * n + j] * x[j];
+            s /= aii;
+            R l = lo[i], h = hi[i];
+            if (fidx[i] >= 0) { h = hi[i] * x[fidx[i]]; l = -h; }
+            if (s > h) s = h;
+            if (s < l) s = l;
+            x[i] = s;
+        }
+}
+
+// ------------------------------------------------------------------------ per-thread contact record
+template <typename R>
+struct ContactSink {      // where the LAST sub-step's contacts go (dartb_get_contacts); may be null
+    int32_t* count;       // [n]
+    int32_t* body;        // [n, maxc]
+    float* data;          // [n, maxc, 10]
+    int maxc;
+};
+
+// ------------------------------------------------------------------------ kinematics only
+// positions/orientations for the task layer (height of a body COM)
+template <class T, typename R>
+DEVI void fk_positions(const PModel<R>& M, const R (&q)[T::NB], R (&cs)[T::NB], R (&sn)[T::NB], R (&px)[T::NB],
+                       R (&py)[T::NB]) {
+    R th[T::NB];
+    static_for<0, T::NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int par = T::parent(i);
+        R cp = 1, sp = 0, ppx = 0, ppy = 0, thp = 0;
+        if constexpr (par >= 0) { cp = cs[par]; sp = sn[par]; ppx = px[par]; ppy = py[par]; thp = th[par]; }
+        const R arx = cp * M.ax[i] - sp * M.ay[i], ary = sp * M.ax[i] + cp * M.ay[i];
+        if constexpr (T::jtype(i) == PM_REV) {
+            th[i] = thp + M.sgn[i] * q[i];
+            Num<R>::sincos_(th[i], &sn[i], &cs[i]);
+            px[i] = ppx + arx; py[i] = ppy + ary;
+        } else {
+            th[i] = thp; cs[i] = cp; sn[i] = sp;
+            const R uwx = cp * M.ux[i] - sp * M.uy[i], uwy = sp * M.ux[i] + cp * M.uy[i];
+            px[i] = ppx + arx + uwx * q[i]; py[i] = ppy + ary + uwy * q[i];
+        }
+    });
+}
+
+// ------------------------------------------------------------------------ one DART time step
+// q, dq: in/out.  tau: generalized forces.  (eft, efx, efy): external spatial force per planar
+// body [torque about the body origin; fx; fy] in world axes (only read when FEXT).
+// FLUID: compute the snake fluid force (snake_7link.py:35-47) from the pre-step state instead.
+template <class T, typename R, bool FEXT, bool FLUID>
+DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&tau)[T::NB], const R (&eft)[T::NB],
+                  const R (&efx)[T::NB], const R (&efy)[T::NB], R fluid_offset, R fluid_coef, int lcp_mode,
+                  int pgs_iters, const ContactSink<R>* sink, int world) {
+    constexpr int NB = T::NB, NS = T::NS, NR = T::NR;
+    const R dt = M.dt;
+    // ---------------- K1: forward kinematics, velocities, partial accelerations
+    R th[NB], cs[NB], sn[NB], px[NB], py[NB], rx[NB], ry[NB], wz[NB], vx[NB], vy[NB], ex[NB], ey[NB], uwx[NB], uwy[NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int par = T::parent(i);
+        R cp = 1, sp = 0, ppx = 0, ppy = 0, wp = 0, vpx = 0, vpy = 0, thp = 0;
+        if constexpr (par >= 0) { cp = cs[par]; sp = sn[par]; ppx = px[par]; ppy = py[par]; wp = wz[par]; vpx = vx[par]; vpy = vy[par]; thp = th[par]; }
+        const R arx = cp * M.ax[i] - sp * M.ay[i], ary = sp * M.ax[i] + cp * M.ay[i];
+        if constexpr (T::jtype(i) == PM_REV) {
+            th[i] = thp + M.sgn[i] * q[i];
+            Num<R>::sincos_(th[i], &sn[i], &cs[i]);
+            rx[i] = arx; ry[i] = ary;
+            const R sd = M.sgn[i] * dq[i];
+            wz[i] = wp + sd;
+            vx[i] = vpx - wp * ary; vy[i] = vpy + wp * arx;
+            ex[i] = sd * vy[i]; ey[i] = -sd * vx[i];
+            uwx[i] = 0; uwy[i] = 0;
+        } else {
+            th[i] = thp; cs[i] = cp; sn[i] = sp;
+            uwx[i] = cp * M.ux[i] - sp * M.uy[i]; uwy[i] = sp * M.ux[i] + cp * M.uy[i];
+            rx[i] = arx + uwx[i] * q[i]; ry[i] = ary + uwy[i] * q[i];
+            wz[i] = wp;
+            vx[i] = vpx - wp * ry[i] + uwx[i] * dq[i]; vy[i] = vpy + wp * rx[i] + uwy[i] * dq[i];
+            ex[i] = -wp * uwy[i] * dq[i]; ey[i] = wp * uwx[i] * dq[i];
+        }
+        px[i] = ppx + rx[i]; py[i] = ppy + ry[i];
+    });
+
+    // ---------------- K2: bias forces + implicit articulated inertia (leaves -> root)
+    R U0[NB], U1[NB], U2[NB], Di[NB], uu[NB];
+    {
+        R aJ[NB], ahx[NB], ahy[NB], ama[NB], amb[NB], amc[NB], apt[NB], apx[NB], apy[NB];
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            aJ[i] = 0; ahx[i] = 0; ahy[i] = 0; ama[i] = 0; amb[i] = 0; amc[i] = 0; apt[i] = 0; apx[i] = 0; apy[i] = 0;
+        });
+        static_rfor<NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int par = T::parent(i);
+            const R m = M.mass[i];
+            const R dx = cs[i] * M.cx[i] - sn[i] * M.cy[i], dy = sn[i] * M.cx[i] + cs[i] * M.cy[i];
+            R J = M.izz[i] + m * (dx * dx + dy * dy), hx = -m * dy, hy = m * dx, ma = m, mb = 0, mc = m;
+            const R Px = m * (vx[i] - wz[i] * dy), Py = m * (vy[i] + wz[i] * dx);
+            R pt = vx[i] * Py - vy[i] * Px - (dx * m * M.gy - dy * m * M.gx);
+            R pfx = -wz[i] * Py - m * M.gx, pfy = wz[i] * Px - m * M.gy;
+            if constexpr (FEXT) { pt -= eft[i]; pfx -= efx[i]; pfy -= efy[i]; }
+            if constexpr (FLUID) {
+                // bn.com_spatial_velocity(), norm_dir = R*ez, add_ext_force at the body origin
+                const R nx = cs[i] * M.fnx[i] - sn[i] * M.fny[i], ny = sn[i] * M.fnx[i] + cs[i] * M.fny[i];
+                const R vcx = vx[i] - wz[i] * dy, vcy = vy[i] + wz[i] * dx;  // COM velocity (origin = DART origin here)
+                const R crx = -wz[i] * ny, cry = wz[i] * nx;                 // omega x n
+                const R dp = (vcx + crx * fluid_offset) * nx + (vcy + cry * fluid_offset) * ny;
+                const R dn = (vcx - crx * fluid_offset) * nx + (vcy - cry * fluid_offset) * ny;
+                R ffx = 0, ffy = 0;
+                if (dp > 0) { ffx = -fluid_coef * dp * nx; ffy = -fluid_coef * dp * ny; }
+                if (dn < 0) { ffx = -fluid_coef * dn * nx; ffy = -fluid_coef * dn * ny; }
+                const R oxw = cs[i] * M.ox[i] - sn[i] * M.oy[i], oyw = sn[i] * M.ox[i] + cs[i] * M.oy[i];
+                pt -= oxw * ffy - oyw * ffx; pfx -= ffx; pfy -= ffy;
+            }
+            if constexpr (topo_has_child<T>(i)) {
+                J += aJ[i]; hx += ahx[i]; hy += ahy[i]; ma += ama[i]; mb += amb[i]; mc += amc[i];
+                pt += apt[i]; pfx += apx[i]; pfy += apy[i];
+            }
+            const R t0 = hx * ex[i] + hy * ey[i], t1 = ma * ex[i] + mb * ey[i], t2 = mb * ex[i] + mc * ey[i];
+            R D, u;
+            if constexpr (T::jtype(i) == PM_REV) {
+                const R s = M.sgn[i];
+                U0[i] = s * J; U1[i] = s * hx; U2[i] = s * hy;
+                D = J;
+                u = tau[i] - s * (pt + t0);
+            } else {
+                U0[i] = hx * uwx[i] + hy * uwy[i]; U1[i] = ma * uwx[i] + mb * uwy[i]; U2[i] = mb * uwx[i] + mc * uwy[i];
+                D = uwx[i] * U1[i] + uwy[i] * U2[i];
+                u = tau[i] - (uwx[i] * (pfx + t1) + uwy[i] * (pfy + t2));
+            }
+            u += -M.kspring[i] * (q[i] - M.rest[i] + dt * dq[i]) - M.damping[i] * dq[i];
+            D += dt * M.damping[i] + dt * dt * M.kspring[i];
+            const R di = (R)1 / D;
+            Di[i] = di; uu[i] = u;
+            if constexpr (par >= 0) {
+                const R g = u * di;
+                const R pa0 = pt + t0 + U0[i] * g, pa1 = pfx + t1 + U1[i] * g, pa2 = pfy + t2 + U2[i] * g;
+                const R P00 = J - U0[i] * U0[i] * di, P01 = hx - U0[i] * U1[i] * di, P02 = hy - U0[i] * U2[i] * di;
+                const R P11 = ma - U1[i] * U1[i] * di, P12 = mb - U1[i] * U2[i] * di, P22 = mc - U2[i] * U2[i] * di;
+                const R kx = -ry[i], ky = rx[i];
+                const R nhx = P01 + P11 * kx + P12 * ky, nhy = P02 + P12 * kx + P22 * ky;
+                aJ[par] += P00 + kx * (P01 + nhx) + ky * (P02 + nhy);
+                ahx[par] += nhx; ahy[par] += nhy; ama[par] += P11; amb[par] += P12; amc[par] += P22;
+                apt[par] += pa0 + kx * pa1 + ky * pa2; apx[par] += pa1; apy[par] += pa2;
+            }
+        });
+    }
+    // ---------------- K3: accelerations (root -> leaves), dq += dt * ddq
+    {
+        R a0[NB], a1[NB], a2[NB];
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int par = T::parent(i);
+            R p0 = 0, p1 = 0, p2 = 0;
+            if constexpr (par >= 0) { p0 = a0[par]; p1 = a1[par] - a0[par] * ry[i]; p2 = a2[par] + a0[par] * rx[i]; }
+            const R dd = Di[i] * (uu[i] - (U0[i] * p0 + U1[i] * p1 + U2[i] * p2));
+            if constexpr (T::jtype(i) == PM_REV) { a0[i] = p0 + M.sgn[i] * dd; a1[i] = p1 + ex[i]; a2[i] = p2 + ey[i]; }
+            else { a0[i] = p0; a1[i] = p1 + ex[i] + uwx[i] * dd; a2[i] = p2 + ey[i] + uwy[i] * dd; }
+            dq[i] += dt * dd;
+        });
+    }
+
+    // ---------------- K4/K5: collide + constraint rows
+    int n = 0, nc = 0;
+    R Jr[NR * NB], bb[NR], lo[NR], hi[NR];
+    int fidx[NR];
+    R cpx[T::NSA], cpy[T::NSA], cnx[T::NSA], cny[T::NSA], cdep[T::NSA];
+    int crow[T::NSA], cshape[T::NSA];
+    const R INF = Num<R>::inf();
+    if constexpr (NS > 0) {
+        if (M.has_ground) {
+            const R inv_dt = (R)1 / dt;
+            static_for<0, NS>([&](auto sc) {
+                constexpr int s = decltype(sc)::value;
+                constexpr int b = T::sbody(s);
+                const R ccx = px[b] + cs[b] * M.scx[s] - sn[b] * M.scy[s], ccy = py[b] + sn[b] * M.scx[s] + cs[b] * M.scy[s];
+                const R adx = cs[b] * M.sdx[s] - sn[b] * M.sdy[s], ady = sn[b] * M.sdx[s] + cs[b] * M.sdy[s];
+                const R hl = M.shalf[s], rad = M.srad[s];
+                R lx, ly, bx, by;
+                closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy,
+                                        M.ghx, M.ghy, lx, ly, bx, by);
+                const R ddx = lx - bx, ddy = ly - by;
+                const R d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+                if (!(d > rad)) {
+                    R nx, ny, depth, Px, Py;
+                    if (d > 0) {
+                        nx = ddx / d; ny = ddy / d;
+                        depth = rad - d;
+                        const R k = (R)0.5 * (-rad - d);
+                        Px = lx + nx * k; Py = ly + ny * k;
+                    } else {  // axis inside the box: push out through the box's local +y face
+                        nx = M.gupx; ny = M.gupy;
+                        depth = rad + (M.ghup - ((lx - M.gcx) * nx + (ly - M.gcy) * ny));
+                        Px = lx; Py = ly;
+                    }
+                    const R mu = M.smu[s];
+                    const bool fric = mu > (R)DK_FRICTION_THRESHOLD;
+                    const R tx = -ny, ty = nx;  // DART tangent t1 = z x n (in-plane); t2 is out of plane (inert)
+                    const int r0 = n;
+                    R vn = 0, vt = 0;
+                    static_for<0, NB>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        R jn = 0, jt = 0;
+                        if constexpr (topo_is_ancestor<T>(j, b)) {
+                            R ax_, ay_;
+                            if constexpr (T::jtype(j) == PM_REV) { ax_ = -M.sgn[j] * (Py - py[j]); ay_ = M.sgn[j] * (Px - px[j]); }
+                            else { ax_ = uwx[j]; ay_ = uwy[j]; }
+                            jn = ax_ * nx + ay_ * ny; jt = ax_ * tx + ay_ * ty;
+                            vn += jn * dq[j]; vt += jt * dq[j];
+                        }
+                        Jr[r0 * NB + j] = jn;
+                        if (fric) Jr[(r0 + 1) * NB + j] = jt;
+                    });
+                    R bounce = depth;
+                    if (bounce < 0) bounce = 0;
+                    else { bounce *= inv_dt * (R)DK_CONTACT_ERP; if (bounce > (R)DK_CONTACT_MAX_ERV) bounce = (R)DK_CONTACT_MAX_ERV; }
+                    bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1;
+                    n = r0 + 1;
+                    if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; n = r0 + 2; }
+                    cpx[nc] = Px; cpy[nc] = Py; cnx[nc] = nx; cny[nc] = ny; cdep[nc] = depth; crow[nc] = r0 | (fric ? 0x100 : 0);
+                    cshape[nc] = s;
+                    nc++;
+                }
+            });
+        }
+    }
+    const int n_contact_rows = n;
+    // joint-limit rows: q BEFORE this step's integration, dq AFTER the unconstrained update
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (M.limited[i]) {
+            int act = 0;
+            if (q[i] - M.qlo[i] <= 0) act = -1;
+            else if (q[i] - M.qhi[i] >= 0) act = 1;
+            if (act != 0 && n < NR) {
+                static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Jr[n * NB + j] = (j == i) ? (R)1 : (R)0; });
+                bb[n] = -dq[i];
+                if (act < 0) { lo[n] = 0; hi[n] = INF; } else { lo[n] = -INF; hi[n] = 0; }
+                fidx[n] = -1;
+                n++;
+            }
+        }
+    });
+
+    if (n > 0) {
+        // plain (non-implicit) articulated inertia for the impulse passes
+        R V0[NB], V1[NB], V2[NB], Ei[NB];
+        {
+            R aJ[NB], ahx[NB], ahy[NB], ama[NB], amb[NB], amc[NB];
+            static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; aJ[i] = 0; ahx[i] = 0; ahy[i] = 0; ama[i] = 0; amb[i] = 0; amc[i] = 0; });
+            static_rfor<NB>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int par = T::parent(i);
+                const R m = M.mass[i];
+                const R dx = cs[i] * M.cx[i] - sn[i] * M.cy[i], dy = sn[i] * M.cx[i] + cs[i] * M.cy[i];
+                R J = M.izz[i] + m * (dx * dx + dy * dy), hx = -m * dy, hy = m * dx, ma = m, mb = 0, mc = m;
+                if constexpr (topo_has_child<T>(i)) { J += aJ[i]; hx += ahx[i]; hy += ahy[i]; ma += ama[i]; mb += amb[i]; mc += amc[i]; }
+                R D;
+                if constexpr (T::jtype(i) == PM_REV) { const R s = M.sgn[i]; V0[i] = s * J; V1[i] = s * hx; V2[i] = s * hy; D = J; }
+                else {
+                    V0[i] = hx * uwx[i] + hy * uwy[i]; V1[i] = ma * uwx[i] + mb * uwy[i]; V2[i] = mb * uwx[i] + mc * uwy[i];
+                    D = uwx[i] * V1[i] + uwy[i] * V2[i];
+                }
+                const R di = (R)1 / D;
+                Ei[i] = di;
+                if constexpr (par >= 0) {
+                    const R P00 = J - V0[i] * V0[i] * di, P01 = hx - V0[i] * V1[i] * di, P02 = hy - V0[i] * V2[i] * di;
+                    const R P11 = ma - V1[i] * V1[i] * di, P12 = mb - V1[i] * V2[i] * di, P22 = mc - V2[i] * V2[i] * di;
+                    const R kx = -ry[i], ky = rx[i];
+                    const R nhx = P01 + P11 * kx + P12 * ky, nhy = P02 + P12 * kx + P22 * ky;
+                    aJ[par] += P00 + kx * (P01 + nhx) + ky * (P02 + nhy);
+                    ahx[par] += nhx; ahy[par] += nhy; ama[par] += P11; amb[par] += P12; amc[par] += P22;
+                }
+            });
+        }
+        // M^-1 J^T, one impulse pass per row (DART: applyUnitImpulse + getVelocityChange)
+        R MJ[NR * NB];
+        for (int r = 0; r < n; r++) {
+            R rh[NB], ur[NB], apt[NB], apx[NB], apy[NB];
+            static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; rh[i] = Jr[r * NB + i]; apt[i] = 0; apx[i] = 0; apy[i] = 0; });
+            static_rfor<NB>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int par = T::parent(i);
+                R pt = 0, pfx = 0, pfy = 0;
+                if constexpr (topo_has_child<T>(i)) { pt = apt[i]; pfx = apx[i]; pfy = apy[i]; }
+                R u;
+                if constexpr (T::jtype(i) == PM_REV) u = rh[i] - M.sgn[i] * pt;
+                else u = rh[i] - (uwx[i] * pfx + uwy[i] * pfy);
+                ur[i] = u;
+                if constexpr (par >= 0) {
+                    const R g = u * Ei[i];
+                    const R pa0 = pt + V0[i] * g, pa1 = pfx + V1[i] * g, pa2 = pfy + V2[i] * g;
+                    apt[par] += pa0 - ry[i] * pa1 + rx[i] * pa2; apx[par] += pa1; apy[par] += pa2;
+                }
+            });
+            R a0[NB], a1[NB], a2[NB];
+            static_for<0, NB>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int par = T::parent(i);
+                R p0 = 0, p1 = 0, p2 = 0;
+                if constexpr (par >= 0) { p0 = a0[par]; p1 = a1[par] - a0[par] * ry[i]; p2 = a2[par] + a0[par] * rx[i]; }
+                const R dd = Ei[i] * (ur[i] - (V0[i] * p0 + V1[i] * p1 + V2[i] * p2));
+                if constexpr (T::jtype(i) == PM_REV) { a0[i] = p0 + M.sgn[i] * dd; a1[i] = p1; a2[i] = p2; }
+                else { a0[i] = p0; a1[i] = p1 + uwx[i] * dd; a2[i] = p2 + uwy[i] * dd; }
+                MJ[r * NB + i] = dd;
+            });
+        }
+        R A[NR * NR], x[NR];
+        for (int r = 0; r < n; r++)
+            for (int s = 0; s < n; s++) {
+                R v = 0;
+#pragma unroll
+                for (int j = 0; j < NB; j++) v += Jr[s * NB + j] * MJ[r * NB + j];
+                A[r * n + s] = v;
+            }
+        for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
+        if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
+        else lcp_dantzig<R, NR>(n, A, x, bb, lo, hi, fidx);
+        // ---------------- K7: apply impulses
+        for (int r = 0; r < n; r++) {
+            const R xr = x[r];
+#pragma unroll
+            for (int j = 0; j < NB; j++) dq[j] += MJ[r * NB + j] * xr;
+        }
+        if (sink && sink->data) {
+            const R inv_dt = (R)1 / dt;
+            for (int c = 0; c < nc && c < sink->maxc; c++) {
+                const int r0 = crow[c] & 0xff;
+                const R xn = x[r0], xt = (crow[c] & 0x100) ? x[r0 + 1] : (R)0;
+                const R fx = (cnx[c] * xn - cny[c] * xt) * inv_dt, fy = (cny[c] * xn + cnx[c] * xt) * inv_dt;
+                float* o = sink->data + ((size_t)world * sink->maxc + c) * 10;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    o[k] = (float)(M.e1[k] * cpx[c] + M.e2[k] * cpy[c] + M.en[k] * M.hz);
+                    o[3 + k] = (float)(M.e1[k] * cnx[c] + M.e2[k] * cny[c]);
+                    o[7 + k] = (float)(M.e1[k] * fx + M.e2[k] * fy);
+                }
+                o[6] = (float)cdep[c];
+            }
+        }
+    }
+    if (sink) {
+        if (sink->count) sink->count[world] = nc;
+        if (sink->body)
+            for (int c = 0; c < sink->maxc; c++) sink->body[(size_t)world * sink->maxc + c] = c < nc ? M.sorig[cshape[c]] : -1;
+    }
+    // ---------------- integrate positions
+    static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; q[i] += dt * dq[i]; });
+}

@@ -103,7 +103,8 @@ typedef struct dartb_task {
 /* Options for dartb_set_option */
 enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
        DARTB_OPT_PGS_ITERS = 2,
-       DARTB_OPT_FRICTION_ALL = 3 /* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */ };
+       DARTB_OPT_FRICTION_ALL = 3,/* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */
+       DARTB_OPT_MAX_EPISODE_STEPS = 4 /* TimeLimit (gym/wrappers/time_limit.py:14-21); 0 = off */ };
 
 typedef struct dartb_engine* dartb_handle_t;
 
@@ -148,6 +149,8 @@ int dartb_substep_f64(dartb_handle_t h, const double* d_tau, const double* d_fex
 int dartb_get_contacts(dartb_handle_t h, int32_t* d_count, int32_t* d_body, float* d_data,
                        void* stream);
 int32_t dartb_max_contacts(dartb_handle_t h);
+/* info['TimeLimit.truncated'] of the last dartb_step (time_limit.py:18-20): uint8[n] */
+int dartb_get_truncated(dartb_handle_t h, uint8_t* d_out, void* stream);
 
 /* Introspection used by the host wrapper and the tests */
 int32_t dartb_num_worlds(dartb_handle_t h);
