@@ -15,7 +15,7 @@ _EXPORTS = [
     "dartb_get_state", "dartb_set_state_f64", "dartb_get_state_f64", "dartb_step", "dartb_substep",
     "dartb_substep_f64", "dartb_get_contacts", "dartb_get_truncated", "dartb_max_contacts", "dartb_num_worlds",
     "dartb_num_dofs", "dartb_is_f64", "dartb_launch_count", "dartb_kernel_name", "dartb_last_error",
-    "dartb_version",
+    "dartb_version", "dartb_describe",
 ]
 
 
@@ -67,6 +67,7 @@ def load(build_if_missing: bool = True):
         "dartb_kernel_name": (C.c_char_p, [vp]),
         "dartb_last_error": (C.c_char_p, []),
         "dartb_version": (C.c_char_p, []),
+        "dartb_describe": (C.c_int, [C.POINTER(CModel), C.POINTER(CTask), C.c_char_p, i32]),
     }
     for name in _EXPORTS:
         fn = getattr(L, name)
@@ -78,3 +79,13 @@ def load(build_if_missing: bool = True):
 def check(rc: int) -> None:
     if rc != 0:
         raise DartbError(load().dartb_last_error().decode("utf-8", "replace"))
+
+
+def describe(model, task) -> str:
+    """Which kernel specialisation a Model/Task lowers to (host-only, no GPU needed)."""
+    from .cstructs import pack_model, pack_task
+    L = load()
+    cm, ct = pack_model(model), pack_task(task)
+    buf = C.create_string_buffer(256)
+    check(L.dartb_describe(C.byref(cm), C.byref(ct), buf, 256))
+    return buf.value.decode()

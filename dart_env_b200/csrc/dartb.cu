@@ -639,6 +639,15 @@ int32_t dartb_is_f64(dartb_handle_t e) { return e && e->f64 ? 1 : 0; }
 int64_t dartb_launch_count(dartb_handle_t e) { return e ? e->launches : 0; }
 const char* dartb_kernel_name(dartb_handle_t e) { return e ? e->kernel_name.c_str() : ""; }
 const char* dartb_last_error(void) { return g_err.c_str(); }
+
+int dartb_describe(const dartb_model_t* model, const dartb_task_t* task, char* buf, int32_t len) {
+    if (!model || !task || !buf || len < 2) return fail("null argument");
+    dartb_engine e;
+    e.model = *model; e.task = *task;
+    if (lower_into(&e)) return 1;
+    std::snprintf(buf, (size_t)len, "%s nd=%d max_contacts=%d", e.kernel_name.c_str(), e.nd, e.max_contacts);
+    return 0;
+}
 const char* dartb_version(void) { return "dartb 0.1 (sm_100a)"; }
 
 }  // extern "C"

@@ -1,0 +1,220 @@
+"""Batched DartEnv: the host-side mirror of the reference's gym/envs/dart/dart_env.py:DartEnv.
+
+Same constructor arguments (where meaningful), same reset / step / seed / set_state /
+state_vector / dt / do_simulation surface and Box spaces, but `num_envs` independent worlds are
+stepped by one CUDA launch through the C-ABI (libdartb.so) instead of one pydart2 World.step()
+per Python call.  No GL, no pydart2.  There is no CPU fallback: constructing an env without a
+CUDA device raises.
+
+Return types
+  num_envs == 1 and batched=False (the default for gym.make-style use): the reference's own
+      types — obs float64 ndarray [nobs], reward float, done bool, info dict (test_envs.py:27-28).
+  batched=True: VectorEnv conventions (gym/vector/sync_vector_env.py:44-47,73-84) —
+      obs [N, nobs], rewards [N], dones [N] with auto-reset; `output="torch"` keeps everything on
+      the GPU (zero copies), `output="numpy"` returns host arrays through pinned buffers.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .cstructs import Task
+from .engine import Engine
+from .skel import load_model
+from .spaces import Box, batch_space
+
+
+class DartEnv:
+    """Superclass for all (batched) Dart environments."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, model_paths, frame_skip, observation_size, action_bounds, dt=0.002, obs_type="parameter",
+                 action_type="continuous", visualize=True, disableViewer=False, screen_width=80, screen_height=45, *,
+                 task: Optional[Task] = None, num_envs: int = 1, batched: Optional[bool] = None, output: str = "torch",
+                 device: int = 0, seed: Optional[int] = None, world_offset: int = 0, auto_reset: Optional[bool] = None,
+                 max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False):
+        assert obs_type in ("parameter", "image")
+        assert action_type in ("continuous", "discrete")
+        if obs_type == "image":
+            raise NotImplementedError("pixel observations need the GL viewer (out of scope)")
+        if isinstance(model_paths, str):
+            model_paths = [model_paths]
+        if len(model_paths) < 1:
+            raise ValueError("At least one model file is needed.")
+        if not model_paths[0].endswith(".skel"):
+            raise NotImplementedError("URDF/SDF loading (dart_env.py:56-59) is not implemented; no in-tree env uses it")
+        # dart_env.py:54-67: build the world, robot = last skeleton, enforce every limited dof
+        self.model = load_model(model_paths[0], dt)
+        self.model.enforce_limits()
+        if friction_all is not None:
+            for b in self.model.bodies:
+                b.friction_coeff = float(friction_all)
+        if task is None:
+            raise ValueError("a Task (dart_env_b200.cstructs.Task) describing obs/reward/done is required")
+        if task.frame_skip != frame_skip or task.n_obs != observation_size:
+            raise ValueError("task does not match frame_skip / observation_size")
+        self.task = task
+        self.frame_skip = frame_skip
+        self.obs_dim = observation_size
+        self.act_dim = len(action_bounds[0])
+        self.num_envs = int(num_envs)
+        self.batched = (self.num_envs > 1) if batched is None else bool(batched)
+        if not self.batched and self.num_envs != 1:
+            raise ValueError("batched=False needs num_envs == 1")
+        if output not in ("torch", "numpy"):
+            raise ValueError("output must be 'torch' or 'numpy'")
+        self.output = output if self.batched else "numpy"
+        self.auto_reset = self.batched if auto_reset is None else bool(auto_reset)
+        self.world_offset = int(world_offset)
+        self.disableViewer = True
+        self.viewer = None
+        self._device_index = device
+        self._f64 = f64
+
+        self.action_space = Box(np.asarray(action_bounds[1], dtype=np.float64), np.asarray(action_bounds[0], dtype=np.float64))
+        high = np.inf * np.ones(self.obs_dim)
+        self.observation_space = Box(-high, high)
+        self.single_action_space, self.single_observation_space = self.action_space, self.observation_space
+        if self.batched:
+            self.action_space = batch_space(self.single_action_space, self.num_envs)
+            self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+
+        self._seed_value = 0
+        self.engine: Optional[Engine] = None
+        self.seed(seed)
+        self.max_episode_steps = int(max_episode_steps)
+        self.metadata = {"render.modes": [], "video.frames_per_second": int(np.round(1.0 / self.dt))}
+
+    # ------------------------------------------------------------------ engine / buffers
+    def _build_engine(self):
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = Engine(self.model, self.task, self.num_envs, device=self._device_index, seed=self._seed_value,
+                             world_offset=self.world_offset, f64=self._f64)
+        if getattr(self, "max_episode_steps", 0):
+            self.engine.set_max_episode_steps(self.max_episode_steps)
+        dev, n = self.engine.device, self.num_envs
+        self._obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
+        self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
+        self._done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self._act = torch.empty((n, self.act_dim), dtype=torch.float32, device=dev)
+        # pinned host mirrors for the host-facing (numpy) path
+        self._h_act = torch.empty((n, self.act_dim), dtype=torch.float32).pin_memory()
+        self._h_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory()
+        self._h_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
+        self._h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+
+    @property
+    def max_episode_steps(self):
+        return self._max_episode_steps
+
+    @max_episode_steps.setter
+    def max_episode_steps(self, n):
+        self._max_episode_steps = int(n)
+        if self.engine is not None:
+            self.engine.set_max_episode_steps(self._max_episode_steps)
+
+    def seed(self, seed=None):
+        """dart_env.py:117-119.  Reset noise comes from a counter-based generator keyed by
+        (seed, global world id, episode), so results do not depend on sharding."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(4), "little")
+        self._seed_value = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.np_random = np.random.RandomState(self._seed_value & 0xFFFFFFFF)
+        self._build_engine()
+        return [self._seed_value]
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def dt(self):
+        return self.model.dt * self.frame_skip
+
+    def reset(self):
+        obs = self.engine.reset(None, self._obs)
+        return self._out_obs(obs)
+
+    def set_state(self, qpos, qvel):
+        q = torch.as_tensor(np.asarray(qpos, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
+        v = torch.as_tensor(np.asarray(qvel, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
+        assert q.shape == (self.num_envs, self.model.n_dofs) and v.shape == q.shape
+        self.engine.set_state(q.contiguous(), v.contiguous())
+
+    def set_state_vector(self, state):
+        state = np.asarray(state, dtype=np.float64).reshape(self.num_envs, -1)
+        nd = self.model.n_dofs
+        self.set_state(state[:, :nd], state[:, nd:])
+
+    def state_vector(self):
+        q, dq = self.engine.get_state(torch.float64)
+        s = torch.cat([q, dq], dim=1).cpu().numpy()
+        return s if self.batched else s[0]
+
+    def do_simulation(self, tau, n_frames):
+        """dart_env.py:158-175: n_frames x {set_forces(tau); world.step()} (perturbation off)."""
+        t = torch.as_tensor(np.asarray(tau, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
+        t = t.contiguous()
+        for _ in range(n_frames):
+            self.engine.substep(t)
+
+    def step(self, a):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            act = a.reshape(self.num_envs, self.act_dim).to(torch.float32).contiguous()
+            self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)
+        else:
+            self._h_act.copy_(torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim)))
+            self._act.copy_(self._h_act, non_blocking=True)
+            self.engine.step(self._act, self._obs, self._rew, self._done, self.auto_reset)
+        if self.batched and self.output == "torch":
+            return self._obs, self._rew, self._done.bool(), {}
+        self._h_obs.copy_(self._obs, non_blocking=True)
+        self._h_rew.copy_(self._rew, non_blocking=True)
+        self._h_done.copy_(self._done, non_blocking=True)
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        if self.batched:
+            infos = {}
+            if self._max_episode_steps:
+                infos["TimeLimit.truncated"] = self.engine.truncated().cpu().numpy().astype(bool)
+            return (self._h_obs.numpy().copy(), self._h_rew.numpy().astype(np.float64), self._h_done.numpy().astype(np.bool_),
+                    infos)
+        info = {}
+        done = bool(self._h_done[0].item())
+        if self._max_episode_steps:
+            tr = bool(self.engine.truncated()[0].item())
+            if done:
+                info["TimeLimit.truncated"] = tr
+        return self._h_obs.numpy()[0].astype(np.float64), float(self._h_rew[0].item()), done, info
+
+    def _out_obs(self, obs):
+        if self.batched and self.output == "torch":
+            return obs
+        o = obs.cpu().numpy()
+        return o.copy() if self.batched else o[0].astype(np.float64)
+
+    # viewer entry points of the reference that have no meaning without GL
+    def render(self, mode="human", close=False):
+        if close:
+            return None
+        raise NotImplementedError("rendering needs the GL viewer (out of scope, SURVEY.md §2 row 11)")
+
+    def viewer_setup(self):
+        pass
+
+    def contacts(self):
+        """world.collision_result.contacts of the last sub-step: (count[N], body[N,C], data[N,C,10])."""
+        return self.engine.contacts()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,45 @@
+"""The four in-scope task envs (reference gym/envs/dart/{hopper,walker2d,half_cheetah,
+snake_7link}.py) and a gym.make-style registry (gym/envs/__init__.py:202-294)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .dart_env import DartEnv
+from .tasks import SPECS
+
+
+def _make_cls(env_id: str, clsname: str):
+    spec = SPECS[env_id]
+    n_act = spec.task.n_act
+
+    class _Env(DartEnv):
+        __doc__ = "%s (%s), batched on the GPU." % (env_id, spec.skel)
+        spec_id = env_id
+
+        def __init__(self, **kw):
+            self.control_bounds = np.array([[1.0] * n_act, [-1.0] * n_act])
+            self.action_scale = np.array(spec.task.act_scale)
+            kw.setdefault("friction_all", spec.friction_all)
+            DartEnv.__init__(self, spec.skel, spec.task.frame_skip, spec.task.n_obs, self.control_bounds,
+                             dt=spec.dt, disableViewer=True, task=spec.task, **kw)
+
+    _Env.__name__ = _Env.__qualname__ = clsname
+    return _Env
+
+
+DartHopperEnv = _make_cls("DartHopper-v1", "DartHopperEnv")
+DartWalker2dEnv = _make_cls("DartWalker2d-v1", "DartWalker2dEnv")
+DartHalfCheetahEnv = _make_cls("DartHalfCheetah-v1", "DartHalfCheetahEnv")
+DartSnake7LinkEnv = _make_cls("DartSnake7Link-v1", "DartSnake7LinkEnv")
+
+REGISTRY = {"DartHopper-v1": DartHopperEnv, "DartWalker2d-v1": DartWalker2dEnv,
+            "DartHalfCheetah-v1": DartHalfCheetahEnv, "DartSnake7Link-v1": DartSnake7LinkEnv}
+
+
+def make(env_id: str, **kw) -> DartEnv:
+    """gym.make(id): the env wrapped in TimeLimit(max_episode_steps) (registration.py:94-96);
+    here the time limit runs inside the kernel (per-world elapsed counter)."""
+    if env_id not in REGISTRY:
+        raise KeyError("No registered env with id: %s (in scope: %s)" % (env_id, sorted(REGISTRY)))
+    kw.setdefault("max_episode_steps", SPECS[env_id].max_episode_steps)
+    return REGISTRY[env_id](**kw)

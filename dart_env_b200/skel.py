@@ -437,7 +437,8 @@ def find_asset(model_path: str) -> str:
     to an assets dir ($DART_ENV_ASSETS, then the reference checkout if present)."""
     if model_path.startswith("/"):
         return model_path
-    for base in (os.environ.get("DART_ENV_ASSETS"), "/root/reference/gym/envs/dart/assets"):
+    ref = None if os.environ.get("DART_ENV_NO_REFERENCE") else "/root/reference/gym/envs/dart/assets"
+    for base in (os.environ.get("DART_ENV_ASSETS"), ref):
         if base and os.path.exists(os.path.join(base, model_path)):
             return os.path.join(base, model_path)
     return os.path.join(_BUNDLED, model_path)

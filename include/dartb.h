@@ -166,6 +166,10 @@ const char* dartb_kernel_name(dartb_handle_t h);
 int dartb_create_f64(const dartb_model_t* model, const dartb_task_t* task, int32_t n_worlds,
                      int32_t device, uint64_t seed, int64_t world_offset, dartb_handle_t* out);
 
+/* Host-only: lower `model` and report the kernel specialisation it maps to (or fail with the
+ * reason it is out of the planar kernels' scope).  Needs no GPU. */
+int dartb_describe(const dartb_model_t* model, const dartb_task_t* task, char* buf, int32_t len);
+
 const char* dartb_last_error(void);
 const char* dartb_version(void);
 

@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C-ABI, against
+the CPU oracle and the committed golden vectors.
+
+Tolerances (stated, per north_star "fp32 tolerance; bit-exact contact-pair sets and done flags"):
+  fp64 kernel instantiation vs oracle (same algorithm, different formulation):  1e-9 rel
+  fp32 product path, single DART step from identical (q, dq, tau):
+        q   : 2e-6 * (1 + |q|)          dq : 5e-4 * (1 + |dq|)   (contact impulses amplify rounding
+                                               through A^-1, cond(A) up to 1/CFM = 1e5)
+  fp32 env.step (4-5 sub-steps): obs/dq 2e-3 * (1 + |x|), reward 2e-3 * (1 + |r|)
+  contact-pair index sets, limit sets and done flags: bit-exact on every sample that is not
+  within 1e-4 of a contact / limit / termination threshold (those are tagged in the goldens).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dart_env_b200.tasks import SPECS
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
+         "DartHalfCheetah-v1": "halfcheetah.npz", "DartSnake7Link-v1": "snake7link.npz"}
+ENVS = list(SPECS)
+MARGIN = 1e-4
+
+
+def _engine(models, env_id, n, **kw):
+    from dart_env_b200.engine import Engine
+    return Engine(models[env_id], SPECS[env_id].task, n, **kw)
+
+
+def _gold(env_id):
+    return np.load(os.path.join(GOLD, FILES[env_id]))
+
+
+def _substep(models, env_id, g, f64):
+    dev = torch.device("cuda", 0)
+    dt = torch.float64 if f64 else torch.float32
+    n = len(g["sub_q"])
+    eng = _engine(models, env_id, n, f64=f64)
+    eng.set_state(torch.tensor(g["sub_q"], dtype=dt, device=dev), torch.tensor(g["sub_dq"], dtype=dt, device=dev))
+    eng.substep(torch.tensor(g["sub_tau"], dtype=dt, device=dev), torch.tensor(g["sub_fext"], dtype=dt, device=dev).contiguous())
+    q2, dq2 = eng.get_state(torch.float64)
+    cnt, body, data = eng.contacts()
+    torch.cuda.synchronize()
+    out = q2.cpu().numpy(), dq2.cpu().numpy(), cnt.cpu().numpy(), body.cpu().numpy(), data.cpu().numpy()
+    assert eng.launch_count >= 3 and "static:" in eng.kernel_name
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_substep_fp64_matches_oracle_tightly(models, env_id):
+    g = _gold(env_id)
+    q2, dq2, cnt, body, data = _substep(models, env_id, g, True)
+    assert np.allclose(q2, g["sub_q2"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(dq2, g["sub_dq2"], rtol=1e-8, atol=1e-8)
+    safe = (g["sub_contact_margin"] > 1e-9)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
+    mc = min(body.shape[1], g["sub_contact_body"].shape[1])
+    tie_ok = safe & (g["sub_tie_margin"] > 1e-9)
+    assert np.array_equal(body[tie_ok, :mc], g["sub_contact_body"][tie_ok, :mc])
+    # contact geometry + force (pydart2 contact.force), where the tie rule cannot flip the end
+    gd = g["sub_contact_data"][tie_ok][:, :mc]
+    assert np.allclose(data[tie_ok][:, :mc, :7], gd[..., :7], atol=1e-6)
+    assert np.allclose(data[tie_ok][:, :mc, 7:], gd[..., 7:], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_substep_fp32_within_stated_tolerance(models, env_id):
+    g = _gold(env_id)
+    q2, dq2, cnt, body, data = _substep(models, env_id, g, False)
+    safe = (g["sub_contact_margin"] > MARGIN) & (g["sub_limit_margin"] > MARGIN) & (g["sub_tie_margin"] > MARGIN)
+    assert safe.sum() > 0.6 * len(safe)
+    # bit-exact discrete outcomes
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
+    mc = min(body.shape[1], g["sub_contact_body"].shape[1])
+    assert np.array_equal(body[safe, :mc], g["sub_contact_body"][safe, :mc])
+    eq = np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"]))
+    ev = np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"]))
+    assert eq[safe].max() < 2e-6, eq[safe].max()
+    assert ev[safe].max() < 5e-4, ev[safe].max()
+    assert np.median(ev[safe].max(1)) < 2e-6
+
+
+def _envstep(models, env_id, g, f64):
+    dev = torch.device("cuda", 0)
+    dt = torch.float64 if f64 else torch.float32
+    spec = SPECS[env_id]
+    n = len(g["step_q"])
+    eng = _engine(models, env_id, n, f64=f64)
+    eng.set_state(torch.tensor(g["step_q"], dtype=dt, device=dev), torch.tensor(g["step_dq"], dtype=dt, device=dev))
+    obs = torch.empty((n, spec.task.n_obs), dtype=torch.float32, device=dev)
+    rew = torch.empty((n,), dtype=torch.float32, device=dev)
+    done = torch.empty((n,), dtype=torch.uint8, device=dev)
+    eng.step(torch.tensor(g["step_action"], dtype=torch.float32, device=dev), obs, rew, done, auto_reset=False)
+    q2, dq2 = eng.get_state(torch.float64)
+    torch.cuda.synchronize()
+    out = obs.cpu().numpy().astype(np.float64), rew.cpu().numpy().astype(np.float64), done.cpu().numpy().astype(bool), \
+        q2.cpu().numpy(), dq2.cpu().numpy()
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_step_matches_reference_task_layer(models, env_id):
+    """goldens: reference env classes (hopper.py ...) run on the oracle; here the fused kernel."""
+    g = _gold(env_id)
+    fin = np.isfinite(g["step_obs"]).all(1) & np.isfinite(g["step_reward"])
+    # fp64 instantiation: algorithmic equivalence (obs are stored as fp32 at the boundary)
+    obs, rew, done, q2, dq2 = _envstep(models, env_id, g, True)
+    assert np.allclose(q2[fin], g["step_q2"][fin], rtol=1e-7, atol=1e-8)
+    assert np.allclose(dq2[fin], g["step_dq2"][fin], rtol=1e-6, atol=1e-6)
+    assert np.allclose(obs[fin], g["step_obs"][fin], rtol=1e-5, atol=1e-5)
+    assert np.allclose(rew[fin], g["step_reward"][fin], rtol=1e-5, atol=1e-4)
+    safe = g["step_margin"] > 1e-7
+    assert np.array_equal(done[safe], g["step_done"][safe].astype(bool))
+    # fp32 product path
+    obs, rew, done, q2, dq2 = _envstep(models, env_id, g, False)
+    safe = fin & (g["step_margin"] > MARGIN)
+    assert np.array_equal(done[safe], g["step_done"][safe].astype(bool))
+    eo = np.abs(obs - g["step_obs"])[fin] / (1 + np.abs(g["step_obs"][fin]))
+    er = np.abs(rew - g["step_reward"])[fin] / (1 + np.abs(g["step_reward"][fin]))
+    assert np.percentile(eo.max(1), 90) < 2e-3 and np.percentile(er, 90) < 2e-3
+    assert np.median(eo.max(1)) < 1e-5
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_reset_noise_bit_exact_and_sharding_independent(models, env_id):
+    from oracle import oracle as orc
+    spec = SPECS[env_id]
+    n = 64
+    eng = _engine(models, env_id, n, seed=1234, world_offset=1000)
+    obs = eng.reset().cpu().numpy()
+    q, dq = eng.get_state(torch.float64)
+    q, dq = q.cpu().numpy(), dq.cpu().numpy()
+    for w in (0, 1, 17, 63):
+        e = orc.OracleEnv(models[env_id], spec.task, seed=1234, world_id=1000 + w)
+        o = e.reset()
+        oq, odq = e.world.get_state()
+        assert np.array_equal(q[w], oq) and np.array_equal(dq[w], odq)  # bit-exact noise
+        assert np.allclose(obs[w], o, atol=1e-6)
+    assert np.abs(q - models[env_id].q_init()).max() <= 0.005 * (1 + 1e-6)
+    # a second engine holding only worlds 1032.. reproduces the same states (sharding independence)
+    eng2 = _engine(models, env_id, 32, seed=1234, world_offset=1032)
+    eng2.reset()
+    q2, _ = eng2.get_state(torch.float64)
+    assert np.array_equal(q2.cpu().numpy(), q[32:])
+    # second episode differs from the first; masked reset only touches masked worlds
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    eng.reset(mask)
+    q3, _ = eng.get_state(torch.float64)
+    q3 = q3.cpu().numpy()
+    assert np.array_equal(q3[1::2], q[1::2]) and not np.array_equal(q3[::2], q[::2])
+    eng.close(); eng2.close()
+
+
+def test_pgs_mode_matches_oracle_pgs(models):
+    """contact-rich PGS path (BASELINE config 3): same sweep count -> same iterate."""
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    g = _gold(env_id)
+    idx = np.where((g["sub_ncontact"] > 0) & (g["sub_contact_margin"] > MARGIN) & (g["sub_tie_margin"] > MARGIN)
+                   & (g["sub_limit_margin"] > MARGIN))[0][:40]
+    dev = torch.device("cuda", 0)
+    for iters in (1, 4, 30):
+        ref = []
+        w = orc.OracleWorld(models[env_id])
+        w.set_option(1, 1); w.set_option(2, iters)
+        for i in idx:
+            w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+            ref.append(np.concatenate(w.get_state()))
+        ref = np.array(ref)
+        eng = _engine(models, env_id, len(idx), f64=True)
+        eng.set_lcp(1, iters)
+        eng.set_state(torch.tensor(g["sub_q"][idx], device=dev), torch.tensor(g["sub_dq"][idx], device=dev))
+        eng.substep(torch.tensor(g["sub_tau"][idx], device=dev))
+        q2, dq2 = eng.get_state(torch.float64)
+        got = torch.cat([q2, dq2], 1).cpu().numpy()
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-8)
+        eng.close()
+
+
+def test_full_size_properties_hopper_4096(models):
+    """BASELINE config 2 size: determinism, batch == singles, auto-reset semantics, flags."""
+    env_id, n = "DartHopper-v1", 4096
+    spec = SPECS[env_id]
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev); gen.manual_seed(7)
+    acts = [torch.rand((n, 3), generator=gen, device=dev) * 2.6 - 1.3 for _ in range(30)]
+
+    def run(nw, off):
+        eng = _engine(models, env_id, nw, seed=5, world_offset=off)
+        obs = eng.reset()
+        rew = torch.empty((nw,), dtype=torch.float32, device=dev); done = torch.empty((nw,), dtype=torch.uint8, device=dev)
+        tot_done = 0
+        hist = []
+        for a in acts:
+            eng.step(a[off:off + nw].contiguous(), obs, rew, done, True)
+            hist.append((obs.clone(), rew.clone(), done.clone()))
+            tot_done += int(done.sum())
+        q, dq = eng.get_state()
+        eng.close()
+        return hist, q, dq, tot_done
+
+    h1, q1, dq1, nd1 = run(n, 0)
+    h2, q2, dq2, nd2 = run(n, 0)
+    assert torch.equal(q1, q2) and torch.equal(dq1, dq2) and nd1 == nd2 and nd1 > n  # many episodes ended
+    for (o1, r1, d1), (o2, r2, d2) in zip(h1, h2):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    # shard of worlds [1024, 1024+96) stepped alone gives bit-identical results
+    h3, q3, dq3, _ = run(96, 1024)
+    assert torch.equal(q3, q1[1024:1120]) and torch.equal(dq3, dq1[1024:1120])
+    assert torch.equal(h3[-1][0], h1[-1][0][1024:1120])
+    # everything finite, obs of done worlds is a reset obs (|q - q0| <= noise)
+    o, r, d = h1[-1]
+    assert torch.isfinite(o).all() and torch.isfinite(r).all()
+    dm = d.bool()
+    if dm.any():
+        assert (o[dm][:, 1:5].abs() <= 0.005001).all() and ((o[dm][:, 0] - 1.25).abs() < 0.011).all()
+
+
+def test_time_limit_truncation(models):
+    from dart_env_b200.envs import make
+    env = make("DartSnake7Link-v1", num_envs=8, output="numpy", seed=0, max_episode_steps=5)
+    env.reset()
+    for t in range(5):
+        obs, rew, done, info = env.step(np.zeros((8, 6), dtype=np.float32))
+        assert done.all() == (t == 4)
+    assert info["TimeLimit.truncated"].all()
+    obs, rew, done, info = env.step(np.zeros((8, 6), dtype=np.float32))
+    assert not done.any()
+    env.close()
+
+
+def test_gym_surface_single_env_types(models):
+    """test_envs.py:10-37 shape/type contract for the N = 1 adapter (BASELINE config 1 plumbing)."""
+    from dart_env_b200.envs import make
+    for env_id in ENVS:
+        env = make(env_id, seed=0)
+        ob = env.reset()
+        assert env.observation_space.contains(ob) and ob.dtype == np.float64
+        env.action_space.seed(0)
+        a = env.action_space.sample()
+        assert env.action_space.contains(a)
+        ob, r, d, info = env.step(a)
+        assert env.observation_space.contains(ob) and np.isscalar(r) and isinstance(d, bool) and isinstance(info, dict)
+        assert env.dt == pytest.approx(SPECS[env_id].dt * SPECS[env_id].task.frame_skip)
+        s = env.state_vector()
+        assert s.shape == (2 * env.model.n_dofs,)
+        # determinism (test_determinism.py): same seed, same actions -> identical obs
+        env2 = make(env_id, seed=0)
+        ob2 = env2.reset()
+        ob2, r2, d2, _ = env2.step(a)
+        assert np.array_equal(ob, ob2) and r == r2 and d == d2
+        # do_simulation == frame_skip explicit sub-steps (dart_env.py:158-175)
+        env.set_state(s[:env.model.n_dofs], s[env.model.n_dofs:])
+        tau = np.zeros(env.model.n_dofs)
+        env.do_simulation(tau, env.frame_skip)
+        assert np.isfinite(env.state_vector()).all()
+        env.close(); env2.close()
+
+
+def test_contacts_readback_walker(models):
+    from dart_env_b200.envs import make
+    env = make("DartWalker2d-v1", num_envs=256, output="torch", seed=3)
+    env.reset()
+    for _ in range(80):
+        env.step(torch.zeros((256, 6), device="cuda"))
+    cnt, body, data = env.contacts()
+    assert int(cnt.max()) >= 1
+    w = int(torch.argmax(cnt))
+    c = int(cnt[w])
+    assert (body[w, :c] >= 2).all() and (body[w, c:] == -1).all()
+    f = data[w, :c, 7:10]
+    assert (f[:, 1] >= -1e-3).all() and f[:, 1].sum() > 1.0  # ground pushes up
+    assert torch.allclose(data[w, :c, 3:6].norm(dim=1), torch.ones(c, device="cuda"), atol=1e-5)
+    env.close()
