@@ -141,7 +141,7 @@ DEVI float reset_uniform(uint64_t seed, int64_t world, uint32_t episode, int i) 
 // ODE dClosestLineBoxPoints restricted to the plane (the out-of-plane axis has v = 0, region 0).
 // Exact minimiser of the convex piecewise-quadratic distance along p1->p2; ties -> t = 0 (p1).
 template <typename R>
-DEVI void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R hy, R& lx, R& ly, R& bx, R& by) {
+DEVI void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R hy, R& lx, R& ly, R& ddx, R& ddy) {
     R s[2] = {p1x - cx, p1y - cy}, v[2] = {p2x - p1x, p2y - p1y}, sg[2], v2[2], ta[2];
     const R h[2] = {hx, hy};
     const R dvx = v[0], dvy = v[1];
@@ -183,11 +183,11 @@ DEVI void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R h
     }
     lx = p1x + t * dvx;
     ly = p1y + t * dvy;
-    R q0 = sg[0] * (s[0] + t * v[0]), q1 = sg[1] * (s[1] + t * v[1]);
-    q0 = q0 < -hx ? -hx : (q0 > hx ? hx : q0);
-    q1 = q1 < -hy ? -hy : (q1 > hy ? hy : q1);
-    bx = q0 + cx;
-    by = q1 + cy;
+    // (line point) - (box point), formed in box coordinates so it is EXACTLY zero when the line
+    // point is inside the box (ODE forms both points in world coordinates and tests d < 1e-15)
+    const R q0 = sg[0] * (s[0] + t * v[0]), q1 = sg[1] * (s[1] + t * v[1]);
+    ddx = q0 - (q0 < -hx ? -hx : (q0 > hx ? hx : q0));
+    ddy = q1 - (q1 < -hy ? -hy : (q1 > hy ? hy : q1));
 }
 
 // ------------------------------------------------------------------------ K6: boxed LCP
@@ -499,14 +499,13 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 const R ccx = px[b] + cs[b] * M.scx[s] - sn[b] * M.scy[s], ccy = py[b] + sn[b] * M.scx[s] + cs[b] * M.scy[s];
                 const R adx = cs[b] * M.sdx[s] - sn[b] * M.sdy[s], ady = sn[b] * M.sdx[s] + cs[b] * M.sdy[s];
                 const R hl = M.shalf[s], rad = M.srad[s];
-                R lx, ly, bx, by;
+                R lx, ly, ddx, ddy;
                 closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy,
-                                        M.ghx, M.ghy, lx, ly, bx, by);
-                const R ddx = lx - bx, ddy = ly - by;
+                                        M.ghx, M.ghy, lx, ly, ddx, ddy);
                 const R d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
                 if (!(d > rad)) {
                     R nx, ny, depth, Px, Py;
-                    if (d > 0) {
+                    if (!(d < (R)1e-15)) {  // ODE dCollideCapsuleBox mindist (double build)
                         nx = ddx / d; ny = ddy / d;
                         depth = rad - d;
                         const R k = (R)0.5 * (-rad - d);

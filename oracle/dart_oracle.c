@@ -516,8 +516,8 @@ static int sphere_point_contact(const double pl[3], double r, const double pb[3]
                                 double normal[3], double* depth) {
     double dv[3] = {pl[0] - pb[0], pl[1] - pb[1], pl[2] - pb[2]};
     double d = sqrt(v3dot(dv, dv));
+    if (d < 1e-15) return -1; /* ODE dCollideCapsuleBox: mindist (double build) -> box-box fallback */
     if (d > r) return 0;
-    if (d <= 0) return -1;
     for (int i = 0; i < 3; i++) normal[i] = dv[i] / d;
     double k = 0.5 * (-r - d);
     for (int i = 0; i < 3; i++) pos[i] = pl[i] + normal[i] * k;
