@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <algorithm>
 #include <string>
@@ -108,7 +109,7 @@ DEVI void reset_state(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int6
 
 // ------------------------------------------------------------------------ env.step() kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -215,7 +216,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
 
 // ------------------------------------------------------------------------ reset kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -253,7 +254,7 @@ k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K,
 // ------------------------------------------------------------------------ single DART step kernel
 // exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175) with optional ext forces
 template <class T, typename R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, const R* fext /*[n,nbd,3]*/,
           int lcp_mode, int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
     constexpr int NB = T::NB;
@@ -380,7 +381,14 @@ template <> struct Sel<double> {
     static const PTask<double>& t(const dartb_engine* e) { return e->td; }
 };
 
-static int block_for(int n) { return n <= 148 * 32 * 4 ? 32 : (n <= 148 * 64 * 8 ? 64 : 128); }
+static int block_for(int n) {
+    // One warp per SM cannot hide instruction-fetch latency of the unrolled stepper (ncu: stall_no_inst
+    // dominant); several warps per SM share the instruction stream.  DARTB_BLOCK overrides (experiments).
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("DARTB_BLOCK"); forced = e ? atoi(e) : 0; }
+    if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+    return n <= 148 * 32 * 4 ? 32 : (n <= 148 * 64 * 8 ? 64 : 128);
+}
 
 template <typename R>
 static StepArgs<R> make_args(dartb_engine* e) {

@@ -19,14 +19,22 @@
 // WORLD axes taken at each body's own origin, so parent<->child transforms are pure shifts.
 // Only the LCP (variable row count) uses thread-local memory.
 #pragma once
+#ifdef DARTB_HOST_EMU
+// tools/host_emu: the SAME device code compiled as plain C++ for CPU-side numerics debugging and
+// the no-GPU regression tests.  Never part of libdartb.so; the product has no CPU path.
+#include "../../tools/host_emu/cuda_shims.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <type_traits>
 
 #include "planar_model.h"
 
+#ifndef DEVI
 #define DEVI __device__ __forceinline__
+#endif
 
 // ------------------------------------------------------------------------ static loops
 template <int I, int N, class F>
@@ -100,6 +108,7 @@ template <> struct Num<float> {
     static DEVI float abs_(float x) { return fabsf(x); }
     static DEVI float inf() { return __int_as_float(0x7f800000); }
     static DEVI float inert() { return 1e-14f; }
+    static DEVI float mindist() { return 1e-6f; }   // ODE dCollideCapsuleBox, dSINGLE build
 };
 template <> struct Num<double> {
     static DEVI void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
@@ -107,6 +116,7 @@ template <> struct Num<double> {
     static DEVI double abs_(double x) { return fabs(x); }
     static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static DEVI double inert() { return 1e-14; }
+    static DEVI double mindist() { return 1e-15; }  // ODE dCollideCapsuleBox, dDOUBLE build
 };
 
 // DART constants (ContactConstraint.cpp / JointLimitConstraint.cpp), see oracle/dart_oracle.c
@@ -505,7 +515,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 const R d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
                 if (!(d > rad)) {
                     R nx, ny, depth, Px, Py;
-                    if (!(d < (R)1e-15)) {  // ODE dCollideCapsuleBox mindist (double build)
+                    if (!(d < Num<R>::mindist())) {  // ODE dCollideCapsuleBox: pl == pb up to mindist
                         nx = ddx / d; ny = ddy / d;
                         depth = rad - d;
                         const R k = (R)0.5 * (-rad - d);

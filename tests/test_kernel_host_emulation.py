@@ -1,0 +1,73 @@
+"""No-GPU regression test of the KERNEL SOURCE: tools/host_emu compiles the very same device code
+(dart_env_b200/csrc/planar_kernels.cuh + lower.h) as plain C++ and steps the golden (q, dq, tau)
+triples on the CPU.  The fp64 instantiation must agree with the 3-D fp64 oracle to 1e-9 (the
+planar/weld-merged formulation is algebraically the same step); the fp32 instantiation must
+stay inside the tolerance the GPU test states.  This is a test tool, not a product fallback:
+libdartb.so contains no host path."""
+import os
+
+import numpy as np
+import pytest
+
+from dart_env_b200.tasks import SPECS
+from tools.host_emu import emu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
+         "DartHalfCheetah-v1": "halfcheetah.npz", "DartSnake7Link-v1": "snake7link.npz"}
+
+
+def _run(models, env_id, f64, **kw):
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    mc = 8
+    out = emu.substep(models[env_id], SPECS[env_id].task, g["sub_q"], g["sub_dq"], g["sub_tau"], g["sub_fext"],
+                      f64=f64, maxc=mc, **kw)
+    return g, out
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_kernel_source_fp64_equals_oracle(models, env_id):
+    g, (q2, dq2, cnt, body, data) = _run(models, env_id, True)
+    assert np.allclose(q2, g["sub_q2"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(dq2, g["sub_dq2"], rtol=1e-8, atol=1e-8)
+    safe = g["sub_contact_margin"] > 1e-9
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
+    tie_ok = safe & (g["sub_tie_margin"] > 1e-9)
+    assert np.array_equal(body[tie_ok], g["sub_contact_body"][tie_ok])
+    assert np.allclose(data[tie_ok][..., :7], g["sub_contact_data"][tie_ok][..., :7], atol=1e-6)
+    assert np.allclose(data[tie_ok][..., 7:], g["sub_contact_data"][tie_ok][..., 7:], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_kernel_source_fp32_within_tolerance(models, env_id):
+    g, (q2, dq2, cnt, body, data) = _run(models, env_id, False)
+    safe = (g["sub_contact_margin"] > 1e-4) & (g["sub_limit_margin"] > 1e-4) & (g["sub_tie_margin"] > 1e-4)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
+    assert np.array_equal(body[safe], g["sub_contact_body"][safe])
+    ev = (np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"])))[safe].max(1)
+    eq = (np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"])))[safe].max(1)
+    assert np.median(ev) < 5e-6 and np.percentile(ev, 99) < 5e-4 and ev.max() < 5e-2 and eq.max() < 2e-4
+
+
+def test_kernel_source_pgs_equals_oracle_pgs(models):
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    idx = np.where(g["sub_ncontact"] > 0)[0][:30]
+    for iters in (1, 5, 30):
+        w = orc.OracleWorld(models[env_id])
+        w.set_option(1, 1); w.set_option(2, iters)
+        ref = []
+        for i in idx:
+            w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+            ref.append(np.concatenate(w.get_state()))
+        q2, dq2, *_ = emu.substep(models[env_id], SPECS[env_id].task, g["sub_q"][idx], g["sub_dq"][idx], g["sub_tau"][idx],
+                                  f64=True, lcp_mode=1, pgs_iters=iters)
+        assert np.allclose(np.concatenate([q2, dq2], 1), np.array(ref), rtol=1e-8, atol=1e-8)
+
+
+def test_reset_noise_generator_matches_oracle():
+    from oracle import oracle as orc
+    L = emu.lib()
+    for seed, w, ep, i in [(0, 0, 0, 0), (1234, 1017, 3, 7), (2 ** 40 + 5, 2 ** 33, 9, 17)]:
+        assert L.emu_reset_uniform(seed, w, ep, i) == orc.reset_uniform(seed, w, ep, i)

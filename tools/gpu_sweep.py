@@ -1,0 +1,45 @@
+"""Developer sweep (under gpurun): step time vs block size / world count.  Each configuration runs
+in a fresh process because DARTB_BLOCK is read once."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = r'''
+import sys, os
+sys.path.insert(0, %r)
+import torch
+from dart_env_b200.envs import make
+env_id, n = sys.argv[1], int(sys.argv[2])
+env = make(env_id, num_envs=n, output="torch", seed=1, batched=True)
+eng = env.engine
+dev = eng.device
+obs = env.reset()
+gen = torch.Generator(device=dev); gen.manual_seed(1234)
+nact = eng.n_act
+acts = [torch.rand((n, nact), generator=gen, device=dev) * 2 - 1 for _ in range(16)]
+for i in range(50): eng.step(acts[i %% 16], env._obs, env._rew, env._done, True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 300
+e0.record()
+for i in range(K): eng.step(acts[i %% 16], env._obs, env._rew, env._done, True)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+print("%%-20s n=%%7d block=%%4s  %%8.1f us/step  %%.3e env-steps/s" %% (env_id, n, os.environ.get("DARTB_BLOCK", "auto"), ms * 1e3, n / (ms * 1e-3)))
+''' % ROOT
+
+cfgs = []
+for b in ("32", "64", "128", "256"):
+    cfgs.append(("DartHopper-v1", 4096, b))
+for n in (16384, 65536, 262144):
+    for b in ("64", "128", "256"):
+        cfgs.append(("DartHopper-v1", n, b))
+for b in ("32", "128", "256"):
+    cfgs.append(("DartWalker2d-v1", 16384, b))
+    cfgs.append(("DartHalfCheetah-v1", 16384, b))
+    cfgs.append(("DartSnake7Link-v1", 4096, b))
+for env_id, n, b in cfgs:
+    env = dict(os.environ, DARTB_BLOCK=b, DART_ENV_NO_REFERENCE="1")
+    r = subprocess.run([sys.executable, "-c", CODE, env_id, str(n)], env=env, capture_output=True, text=True)
+    print((r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)

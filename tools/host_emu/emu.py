@@ -1,0 +1,45 @@
+"""ctypes wrapper for tools/host_emu/libhost_emu.so: the product's device code compiled for the
+CPU (debug + no-GPU regression tests).  Not a product path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from dart_env_b200.cstructs import CModel, CTask, pack_model, pack_task
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-C", _HERE, "libhost_emu.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(os.path.join(_HERE, "libhost_emu.so"))
+        L.emu_last_error.restype = C.c_char_p
+        L.emu_reset_uniform.restype = C.c_float
+        L.emu_reset_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_iters=30, maxc=8):
+    L = lib()
+    cm, ct = pack_model(model), pack_task(task)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    dq = np.ascontiguousarray(dq, dtype=np.float64)
+    n, nd = q.shape
+    dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+    tau = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+    fext = None if fext is None else np.ascontiguousarray(fext, dtype=np.float64)
+    q2, dq2 = np.zeros_like(q), np.zeros_like(dq)
+    cnt = np.zeros(n, dtype=np.int32)
+    body = -np.ones((n, maxc), dtype=np.int32)
+    data = np.zeros((n, maxc, 10), dtype=np.float32)
+    rc = L.emu_substep(C.byref(cm), C.byref(ct), int(f64), n, dp(q), dp(dq), dp(tau), dp(fext), lcp_mode, pgs_iters,
+                       dp(q2), dp(dq2), cnt.ctypes.data_as(C.POINTER(C.c_int32)), body.ctypes.data_as(C.POINTER(C.c_int32)),
+                       data.ctypes.data_as(C.POINTER(C.c_float)), maxc)
+    if rc:
+        raise RuntimeError(L.emu_last_error().decode())
+    return q2, dq2, cnt, body, data
