@@ -19,6 +19,7 @@
 #include "../../include/dartb.h"
 #include "lower.h"
 #include "planar_kernels.cuh"
+#include "planar_loop.cuh"
 
 // ------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -295,6 +296,184 @@ k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* ta
     });
 }
 
+
+// ======================================================================== loop (generic) variant
+// Same kernels built on planar_loop.cuh: runtime topology, small instruction footprint.
+template <typename R>
+DEVI R body_height_loop(const PModel<R>& M, const PTask<R>& K, const R* q) {
+    R cs[LOOP_MAXB], sn[LOOP_MAXB], px[LOOP_MAXB], py[LOOP_MAXB];
+    fk_positions_loop<R>(M, q, cs, sn, px, py);
+    const int i = K.height_body;
+    const R X = px[i] + cs[i] * K.hcx - sn[i] * K.hcy, Y = py[i] + sn[i] * K.hcx + cs[i] * K.hcy;
+    return K.wy1 * X + K.wy2 * Y + K.wy0;
+}
+template <typename R>
+DEVI void write_obs_loop(const PModel<R>& M, const PTask<R>& K, const R* q, const R* dq, float* so) {
+    const int nb = M.nb;
+    so[0] = (K.obs_mode == DARTB_OBS_HEIGHT_Q2_DQ) ? (float)body_height_loop<R>(M, K, q) : (float)q[1];
+    for (int i = 2; i < nb; i++) so[i - 1] = (float)q[i];
+    for (int i = 0; i < nb; i++) {
+        R v = dq[i];
+        if (K.dq_clip > 0) v = v > K.dq_clip ? K.dq_clip : (v < -K.dq_clip ? -K.dq_clip : v);
+        so[nb - 1 + i] = (float)v;
+    }
+}
+template <typename R>
+DEVI void reset_state_loop(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int64_t gw, uint32_t ep, R* q, R* dq) {
+    const int nb = M.nb;
+    const float noise = (float)K.reset_noise;
+    for (int i = 0; i < nb; i++) {
+        const float a = __fmul_rn(reset_uniform(seed, gw, ep, i), noise);
+        const float b = __fmul_rn(reset_uniform(seed, gw, ep, nb + i), noise);
+        q[i] = (R)__fadd_rn((float)M.qinit[i], a);
+        dq[i] = (R)__fadd_rn((float)M.dqinit[i], b);
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    extern __shared__ float smem[];
+    const int nb = M.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane, cnt = min(32, a.n - wb);
+    const bool active = w < a.n;
+    const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
+    float* sw = smem + warp * 32 * stage;
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
+    R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB];
+    R a2 = 0;
+    if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[lane * K.n_act + j]; a2 += v * v; }
+    for (int i = 0; i < nb; i++) {
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+        R t = 0;
+        if (active && K.dof_act[i] >= 0) {
+            R v = (R)sw[lane * K.n_act + K.dof_act[i]];
+            v = v > K.dof_hi[i] ? K.dof_hi[i] : v;
+            v = v < K.dof_lo[i] ? K.dof_lo[i] : v;
+            t = v * K.dof_scale[i];
+        }
+        tau[i] = t;
+    }
+    __syncwarp();
+    const R posbefore = q[0];
+    for (int f = 0; f < K.frame_skip; f++) {
+        const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? &a.sink : nullptr;
+        substep_loop<R>(M, q, dq, tau, false, tau, tau, tau, K.fluid_force != 0, K.fluid_offset, K.fluid_coef, a.lcp_mode,
+                        a.pgs_iters, sk, w);
+    }
+    const R ang = q[2];
+    R r = (q[0] - posbefore) * K.inv_dt_env * K.vel_weight;
+    r += K.alive_bonus;
+    r -= K.ctrl_cost * a2;
+    if (K.limit_pen_dof >= 0) {
+        const int i = K.limit_pen_dof;
+        R pen = 0;
+        if ((M.qlo[i] - q[i]) > -K.limit_pen_margin) pen += (R)1.5;
+        if ((M.qhi[i] - q[i]) < K.limit_pen_margin) pen += (R)1.5;
+        r -= K.limit_pen_weight * pen;
+    }
+    r -= K.dev_cost * Num<R>::abs_(ang);
+    bool ok = true;
+    for (int i = 0; i < nb; i++) {
+        if (i >= 2 && !(Num<R>::abs_(q[i]) < K.state_bound)) ok = false;
+        if (i < 2 && !(Num<R>::abs_(q[i]) < Num<R>::inf())) ok = false;
+        if (!(Num<R>::abs_(dq[i]) < K.state_bound)) ok = false;
+    }
+    if (K.zero_reward_on_blowup && !ok) r = 0;
+    if (K.height_body >= 0) {
+        const R h = body_height_loop<R>(M, K, q);
+        ok = ok && (h > K.height_lo) && (h < K.height_hi);
+    }
+    ok = ok && (Num<R>::abs_(ang) < K.ang_max);
+    bool done = !ok, trunc = false;
+    if (active && a.max_episode_steps > 0) {
+        const int el = a.elapsed[w] + 1;
+        if (el >= a.max_episode_steps) { trunc = !done; done = true; }
+        a.elapsed[w] = (done && a.auto_reset) ? 0 : el;
+    }
+    if (active && done && a.auto_reset) {
+        const uint32_t ep = a.episode[w];
+        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+    }
+    if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
+    __syncwarp();
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (active) {
+        for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
+        a.reward[w] = (float)r;
+        a.done[w] = done ? 1 : 0;
+        if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    extern __shared__ float smem[];
+    const int nb = M.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane, cnt = min(32, a.n - wb);
+    const bool active = w < a.n;
+    float* sw = smem + warp * 32 * K.n_obs;
+    R q[LOOP_MAXB], dq[LOOP_MAXB];
+    const bool doit = active && (a.mask == nullptr || a.mask[w]);
+    for (int i = 0; i < nb; i++) {
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+    }
+    if (doit) {
+        const uint32_t ep = a.episode[w];
+        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+        a.elapsed[w] = 0;
+        for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
+        if (a.sink.count) a.sink.count[w] = 0;
+    }
+    if (a.obs) {
+        if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
+        __syncwarp();
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in, const R* fext, int lcp_mode,
+               int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
+    const int nb = M.nb;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB], eft[LOOP_MAXB], efx[LOOP_MAXB], efy[LOOP_MAXB];
+    for (int i = 0; i < nb; i++) {
+        q[i] = qs[(size_t)i * n + w];
+        dq[i] = dqs[(size_t)i * n + w];
+        tau[i] = tau_in ? tau_in[(size_t)w * nb + i] : (R)0;
+        eft[i] = 0; efx[i] = 0; efy[i] = 0;
+    }
+    if (fext) {
+        R cs[LOOP_MAXB], sn[LOOP_MAXB], px[LOOP_MAXB], py[LOOP_MAXB];
+        fk_positions_loop<R>(M, q, cs, sn, px, py);
+        for (int k = 0; k < M.nbd; k++) {
+            const R* f = fext + ((size_t)w * M.nbd + k) * 3;
+            const R fx = M.e1[0] * f[0] + M.e1[1] * f[1] + M.e1[2] * f[2];
+            const R fy = M.e2[0] * f[0] + M.e2[1] * f[1] + M.e2[2] * f[2];
+            const int g = M.dgroup[k];
+            const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
+            eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
+        }
+        substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    } else {
+        substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    }
+    for (int i = 0; i < nb; i++) { qs[(size_t)i * n + w] = q[i]; dqs[(size_t)i * n + w] = dq[i]; }
+}
+
 // [n, nd] row-major <-> SoA [nd][n] with precision conversion
 template <typename S, typename D>
 __global__ void k_to_soa(int n, int nd, const S* src, D* dst) {
@@ -328,6 +507,8 @@ struct dartb_engine {
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
     int32_t* ccount = nullptr; int32_t* cbody = nullptr; float* cdata = nullptr;
     int lcp_mode = 0, pgs_iters = 30, max_episode_steps = 0;
+    int variant_request = -1;                 // -1 auto (DARTB_VARIANT env or static if available), 0, 1
+    int variant = 0;                          // 0 = unrolled static topology, 1 = loop / generic topology
     int64_t launches = 0;
     std::string kernel_name;
 };
@@ -356,9 +537,11 @@ static int lower_into(dartb_engine* e) {
     int nlim = 0;
     for (int i = 0; i < res.m.nb; i++) nlim += res.m.limited[i] ? 1 : 0;
     int topo = pick_topo(res.signature, nlim);
-    if (topo < 0)
-        return fail("no kernel instantiation for skeleton topology '" + res.signature +
-                    "' (add it to planar_kernels.cuh; there is no generic or CPU fallback)");
+    if (res.m.ns > LOOP_MAXS || res.m.nb > LOOP_MAXB) return fail("model too large for the planar kernels");
+    static int forced_variant = -1;
+    if (forced_variant < 0) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : 0; }
+    if (topo < 0 || e->variant_request == 1 || (e->variant_request < 0 && forced_variant == 1)) e->variant = 1;
+    else e->variant = 0;
     e->topo = topo;
     e->md = res.m; e->td = res.t;
     lower::convert(res.m, e->mf);
@@ -367,7 +550,8 @@ static int lower_into(dartb_engine* e) {
     e->max_contacts = res.max_contacts;
     e->n_orig_bodies = e->model.n_bodies;
     const char* plane = std::fabs(res.m.en[2]) > 0.5 ? "planar-xy" : (std::fabs(res.m.en[1]) > 0.5 ? "planar-zx" : "planar-yz");
-    e->kernel_name = std::string(plane) + "/static:" + topo_name(topo) + (e->f64 ? "/f64" : "/f32");
+    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string("/static:") + topo_name(topo)) +
+                     (e->f64 ? "/f64" : "/f32");
     return 0;
 }
 
@@ -420,7 +604,8 @@ static int launch_step(dartb_engine* e, const float* action, float* obs, float* 
     const PTask<R>& K = Sel<R>::t(e);
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     const size_t shm = (size_t)(bs / 32) * 32 * stage * sizeof(float);
-    DISPATCH_TOPO(e, R, (k_env_step<T, R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a)));
+    if (e->variant == 1) k_env_step_loop<R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a);
+    else DISPATCH_TOPO(e, R, (k_env_step<T, R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a)));
     e->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -432,7 +617,8 @@ static int launch_reset(dartb_engine* e, const uint8_t* mask, float* obs, cudaSt
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
     const PTask<R>& K = Sel<R>::t(e);
     const size_t shm = (size_t)(bs / 32) * 32 * K.n_obs * sizeof(float);
-    DISPATCH_TOPO(e, R, (k_reset<T, R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a)));
+    if (e->variant == 1) k_reset_loop<R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a);
+    else DISPATCH_TOPO(e, R, (k_reset<T, R><<<grid, bs, shm, st>>>(Sel<R>::m(e), K, a)));
     e->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -442,8 +628,11 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
     ContactSink<R> sink;
     sink.count = e->ccount; sink.body = e->cbody; sink.data = e->cdata; sink.maxc = e->max_contacts;
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
-    DISPATCH_TOPO(e, R, (k_substep<T, R><<<grid, bs, 0, st>>>(Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext,
-                                                             e->lcp_mode, e->pgs_iters, sink)));
+    if (e->variant == 1)
+        k_substep_loop<R><<<grid, bs, 0, st>>>(Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
+    else
+        DISPATCH_TOPO(e, R, (k_substep<T, R><<<grid, bs, 0, st>>>(Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext,
+                                                                 e->lcp_mode, e->pgs_iters, sink)));
     e->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -554,6 +743,10 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             e->pgs_iters = (int)value; return 0;
         case DARTB_OPT_FRICTION_ALL:
             for (int i = 0; i < e->model.n_bodies; i++) e->model.bodies[i].friction_coeff = value;
+            return lower_into(e);
+        case DARTB_OPT_KERNEL_VARIANT:
+            if (value != 0 && value != 1) return fail("kernel variant must be 0 (unrolled) or 1 (loop)");
+            e->variant_request = (int)value;
             return lower_into(e);
         case DARTB_OPT_MAX_EPISODE_STEPS:
             if (value < 0) return fail("bad max_episode_steps");

@@ -17,6 +17,9 @@ FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
          "DartHalfCheetah-v1": "halfcheetah.npz", "DartSnake7Link-v1": "snake7link.npz"}
 
 
+VARIANTS = [0, 1]  # 0 = unrolled per-topology kernel, 1 = loop / topology-generic kernel
+
+
 def _run(models, env_id, f64, **kw):
     g = np.load(os.path.join(GOLD, FILES[env_id]))
     mc = 8
@@ -25,9 +28,10 @@ def _run(models, env_id, f64, **kw):
     return g, out
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("env_id", list(SPECS))
-def test_kernel_source_fp64_equals_oracle(models, env_id):
-    g, (q2, dq2, cnt, body, data) = _run(models, env_id, True)
+def test_kernel_source_fp64_equals_oracle(models, env_id, variant):
+    g, (q2, dq2, cnt, body, data) = _run(models, env_id, True, variant=variant)
     assert np.allclose(q2, g["sub_q2"], rtol=1e-9, atol=1e-10)
     assert np.allclose(dq2, g["sub_dq2"], rtol=1e-8, atol=1e-8)
     safe = g["sub_contact_margin"] > 1e-9
@@ -38,9 +42,10 @@ def test_kernel_source_fp64_equals_oracle(models, env_id):
     assert np.allclose(data[tie_ok][..., 7:], g["sub_contact_data"][tie_ok][..., 7:], rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("env_id", list(SPECS))
-def test_kernel_source_fp32_within_tolerance(models, env_id):
-    g, (q2, dq2, cnt, body, data) = _run(models, env_id, False)
+def test_kernel_source_fp32_within_tolerance(models, env_id, variant):
+    g, (q2, dq2, cnt, body, data) = _run(models, env_id, False, variant=variant)
     safe = (g["sub_contact_margin"] > 1e-4) & (g["sub_limit_margin"] > 1e-4) & (g["sub_tie_margin"] > 1e-4)
     assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
     assert np.array_equal(body[safe], g["sub_contact_body"][safe])

@@ -30,16 +30,17 @@ print("%%-20s n=%%7d block=%%4s  %%8.1f us/step  %%.3e env-steps/s" %% (env_id, 
 ''' % ROOT
 
 cfgs = []
-for b in ("32", "64", "128", "256"):
-    cfgs.append(("DartHopper-v1", 4096, b))
-for n in (16384, 65536, 262144):
-    for b in ("64", "128", "256"):
-        cfgs.append(("DartHopper-v1", n, b))
-for b in ("32", "128", "256"):
-    cfgs.append(("DartWalker2d-v1", 16384, b))
-    cfgs.append(("DartHalfCheetah-v1", 16384, b))
-    cfgs.append(("DartSnake7Link-v1", 4096, b))
-for env_id, n, b in cfgs:
-    env = dict(os.environ, DARTB_BLOCK=b, DART_ENV_NO_REFERENCE="1")
+mode = sys.argv[1] if len(sys.argv) > 1 else "block"
+if mode == "variant":
+    for v in ("0", "1"):
+        for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 65536), ("DartWalker2d-v1", 16384),
+                          ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
+            for b in (("32", "128") if n <= 4096 else ("128",)):
+                cfgs.append((env_id, n, b, v))
+else:
+    for b in ("32", "64", "128", "256"):
+        cfgs.append(("DartHopper-v1", 4096, b, "0"))
+for env_id, n, b, v in cfgs:
+    env = dict(os.environ, DARTB_BLOCK=b, DARTB_VARIANT=v, DART_ENV_NO_REFERENCE="1")
     r = subprocess.run([sys.executable, "-c", CODE, env_id, str(n)], env=env, capture_output=True, text=True)
-    print((r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)
+    print("variant=%s " % v + (r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)

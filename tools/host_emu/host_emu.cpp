@@ -7,6 +7,7 @@
 
 #include "../../dart_env_b200/csrc/lower.h"
 #include "../../dart_env_b200/csrc/planar_kernels.cuh"
+#include "../../dart_env_b200/csrc/planar_loop.cuh"
 
 template <class T, typename R>
 static void run_substep(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
@@ -37,6 +38,35 @@ static void run_substep(const PModel<R>& M, int n, const double* q_in, const dou
     }
 }
 
+template <typename R>
+static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
+                             const double* fext, int lcp_mode, int pgs_iters, double* q_out, double* dq_out,
+                             int32_t* count, int32_t* body, float* data, int maxc) {
+    const int NB = M.nb;
+    for (int w = 0; w < n; w++) {
+        R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB], eft[LOOP_MAXB], efx[LOOP_MAXB], efy[LOOP_MAXB];
+        for (int i = 0; i < NB; i++) { q[i] = (R)q_in[w * NB + i]; dq[i] = (R)dq_in[w * NB + i]; tau[i] = tau_in ? (R)tau_in[w * NB + i] : (R)0; eft[i] = efx[i] = efy[i] = 0; }
+        ContactSink<R> sink;
+        sink.count = count; sink.body = body; sink.data = data; sink.maxc = maxc;
+        if (fext) {
+            R cs[LOOP_MAXB], sn[LOOP_MAXB], px[LOOP_MAXB], py[LOOP_MAXB];
+            fk_positions_loop<R>(M, q, cs, sn, px, py);
+            for (int k = 0; k < M.nbd; k++) {
+                const double* f = fext + ((size_t)w * M.nbd + k) * 3;
+                const R fx = (R)(M.e1[0] * f[0] + M.e1[1] * f[1] + M.e1[2] * f[2]);
+                const R fy = (R)(M.e2[0] * f[0] + M.e2[1] * f[1] + M.e2[2] * f[2]);
+                const int g = M.dgroup[k];
+                const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
+                eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
+            }
+            substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        } else {
+            substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        }
+        for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)q[i]; dq_out[w * NB + i] = (double)dq[i]; }
+    }
+}
+
 static std::string g_err;
 
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
@@ -44,12 +74,17 @@ extern "C" const char* emu_last_error() { return g_err.c_str(); }
 // returns 0 ok; arrays are [n, nd] row-major doubles (converted to the kernel precision inside)
 extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task, int f64, int n, const double* q,
                            const double* dq, const double* tau, const double* fext, int lcp_mode, int pgs_iters,
-                           double* q_out, double* dq_out, int32_t* count, int32_t* body, float* data, int maxc) {
+                           double* q_out, double* dq_out, int32_t* count, int32_t* body, float* data, int maxc, int variant) {
     lower::Result res;
     std::string why = lower::lower_model(*model, *task, res);
     if (!why.empty()) { g_err = why; return 1; }
     PModel<float> mf;
     lower::convert(res.m, mf);
+    if (variant == 1) {
+        if (f64) run_substep_loop<double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);
+        else run_substep_loop<float>(mf, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);
+        return 0;
+    }
 #define RUN(T)                                                                                                          \
     if (res.signature == T::sig) {                                                                                       \
         if (f64) run_substep<T, double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
