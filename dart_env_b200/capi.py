@@ -33,7 +33,7 @@ def load(build_if_missing: bool = True):
     if _LIB is not None:
         return _LIB
     so = _build.SO
-    if build_if_missing:
+    if build_if_missing and not (os.environ.get("DARTB_NO_REBUILD") and os.path.exists(so)):
         try:
             if _build.is_stale():
                 _build.build()

@@ -35,6 +35,12 @@
 #ifndef DEVI
 #define DEVI __device__ __forceinline__
 #endif
+#ifdef DARTB_HOST_EMU
+extern long g_emu_counters[8];  // [0] exact LCP calls [1] solved by lcp_small<4> [2] by lcp_small<8> [3] Dantzig [4] BPP iterations
+#define EMU_COUNT(i, v) (g_emu_counters[i] += (v))
+#else
+#define EMU_COUNT(i, v) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------ static loops
 template <int I, int N, class F>
@@ -322,6 +328,156 @@ DEVI void lcp_dantzig(int n, const R* A, R* x, const R* b, R* lo, R* hi, const i
     if (failed) {  // ODE: "LCP internal error": keep what was solved, finite values only
         for (int i = 0; i < n; i++) if (!(x[i] == x[i]) || Num<R>::abs_(x[i]) == INF) x[i] = 0;
     }
+}
+
+// ------------------------------------------------------------------------ K6 fast path: small n in registers
+// Exact boxed LCP for n <= NM rows by block principal pivoting (Judice & Pires) with a masked
+// dense Cholesky, everything in registers and fully unrolled (no thread-local memory, no
+// data-dependent loops except the pivoting iterations).  The solution of the two-stage problem
+// (frictionless normals first, then friction bounds +-mu*x_n fixed: ODE dSolveLCP semantics) is
+// unique for the positive-definite A = J M^-1 J^T (1 + CFM), so any exact method returns what
+// Dantzig returns; ncu showed the Dantzig loop (thread-local arrays, 3-5 active lanes) to be 50% of
+// the kernel's instructions.  Returns false if it did not converge (caller falls back to Dantzig).
+template <typename R, int NM>
+DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg) {
+    R A[NM][NM], b[NM], lo[NM], hi[NM], x[NM], mu[NM];
+    int fi[NM];
+    unsigned st = 0;  // 2 bits per row: 0 free, 1 at lo, 2 at hi, 3 permanently bound at x = 0
+    const R INF = Num<R>::inf();
+#pragma unroll
+    for (int i = 0; i < NM; i++) {
+        const bool on = i < n;
+        b[i] = on ? bg[i] : (R)0; lo[i] = on ? log_[i] : (R)0; hi[i] = on ? hig[i] : (R)0; fi[i] = on ? fidxg[i] : -1;
+        mu[i] = hi[i];
+        x[i] = 0;
+#pragma unroll
+        for (int j = 0; j < NM; j++) A[i][j] = (on && j < n) ? Ag[i * n + j] : (i == j ? (R)1 : (R)0);
+        unsigned s = 0;
+        if (!on || !(A[i][i] > Num<R>::inert())) s = 3;           // padding / inert row
+        else if (fi[i] >= 0) s = 3;                                 // friction rows wait for stage 2
+        else if (lo[i] > -INF && hi[i] == INF) s = 0;               // start free (sticking / active guess)
+        st |= s << (2 * i);
+    }
+    bool ok = true;
+#pragma unroll 1
+    for (int stage = 0; stage < 2; stage++) {
+        if (stage == 1) {
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                if (fi[i] >= 0 && i < n && A[i][i] > Num<R>::inert()) {
+                    R xn = 0;
+#pragma unroll
+                    for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
+                    const R h = Num<R>::abs_(mu[i] * xn);
+                    hi[i] = h; lo[i] = -h;
+                    st &= ~(3u << (2 * i));
+                    if (h == 0) st |= 3u << (2 * i); else any = true;   // free at first
+                }
+            }
+            if (!any) break;
+        }
+        int best = NM + 1, tries = 3;
+        bool done = false;
+#pragma unroll 1
+        for (int it = 0; it < 12 * NM && !done; it++) {
+            // masked system: free rows keep A, bound rows become identity with rhs = bound value
+            R L[NM][NM], y[NM];
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const unsigned si = (st >> (2 * i)) & 3u;
+                const R xb = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
+                if (si != 0) x[i] = xb;
+            }
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const bool fr = ((st >> (2 * i)) & 3u) == 0;
+                R r = b[i];
+#pragma unroll
+                for (int j = 0; j < NM; j++) {
+                    const bool fj = ((st >> (2 * j)) & 3u) == 0;
+                    if (!fj) r -= A[i][j] * x[j];
+                }
+                y[i] = fr ? r : (R)0;
+            }
+            // Cholesky of the masked matrix (bound rows/cols = identity)
+            bool pd = true;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const bool fr = ((st >> (2 * i)) & 3u) == 0;
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    const bool fj = ((st >> (2 * j)) & 3u) == 0;
+                    R s = (fr && fj) ? A[i][j] : (i == j ? (R)1 : (R)0);
+#pragma unroll
+                    for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+                    if (i == j) { if (!(s > 0)) { pd = false; s = 1; } L[i][i] = (R)1 / Num<R>::sqrt_(s); }
+                    else L[i][j] = s * L[j][j];
+                }
+            }
+            if (!pd) { ok = false; break; }
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                R s = y[i];
+#pragma unroll
+                for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+                y[i] = s * L[i][i];
+            }
+#pragma unroll
+            for (int i = NM - 1; i >= 0; i--) {
+                R s = y[i];
+#pragma unroll
+                for (int k = i + 1; k < NM; k++) s -= L[k][i] * y[k];
+                y[i] = s * L[i][i];
+            }
+#pragma unroll
+            for (int i = 0; i < NM; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
+            // infeasibilities
+            unsigned bad = 0;  // bit i set: row i must change set
+            int nbad = 0;
+            unsigned nst = st;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const unsigned si = (st >> (2 * i)) & 3u;
+                if (si == 3) continue;
+                if (si == 0) {
+                    if (x[i] < lo[i]) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
+                    else if (x[i] > hi[i]) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
+                } else {
+                    R w = -b[i];
+#pragma unroll
+                    for (int j = 0; j < NM; j++) w += A[i][j] * x[j];
+                    if ((si == 1 && w < 0) || (si == 2 && w > 0)) {
+                        if (lo[i] < hi[i]) { bad |= 1u << i; nbad++; nst = nst & ~(3u << (2 * i)); }
+                    }
+                }
+            }
+            EMU_COUNT(4, 1);
+            if (nbad == 0) { done = true; break; }
+            if (nbad < best) { best = nbad; tries = 3; st = nst; }
+            else if (tries > 0) { tries--; st = nst; }
+            else {  // Murty: flip only the highest-index infeasible row (finite for P-matrices)
+                const int k = 31 - __clz(bad);
+                st = (st & ~(3u << (2 * k))) | (nst & (3u << (2 * k)));
+            }
+        }
+        if (!done) { ok = false; }
+        if (!ok) break;
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < NM; i++) if (i < n) xg[i] = x[i];
+    return true;
+}
+
+// exact LCP: register fast paths for n <= 4 / n <= 8, Dantzig in thread-local memory beyond
+template <typename R, int NR>
+DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int* fidx) {
+    bool ok = false;
+    EMU_COUNT(0, 1);
+    if (n <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
+    else if (n <= 8 && NR > 4) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(2, 1); }
+    if (!ok) { EMU_COUNT(3, 1); lcp_dantzig<R, NR>(n, A, x, b, lo, hi, fidx); }
 }
 
 // fixed-sweep PGS (oracle/dart_oracle.c::orc_solve_lcp_pgs; DART PGSLCPSolver shape)
@@ -647,7 +803,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
             }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
         if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
-        else lcp_dantzig<R, NR>(n, A, x, bb, lo, hi, fidx);
+        else lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx);
         // ---------------- K7: apply impulses
         for (int r = 0; r < n; r++) {
             const R xr = x[r];

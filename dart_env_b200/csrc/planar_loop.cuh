@@ -299,7 +299,7 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
             }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
         if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
-        else lcp_dantzig<R, NR>(n, A, x, bb, lo, hi, fidx);
+        else lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx);
         for (int r = 0; r < n; r++) {
             const R xr = x[r];
             for (int j = 0; j < nb; j++) dq[j] += MJ[r * MB + j] * xr;

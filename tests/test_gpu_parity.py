@@ -49,7 +49,7 @@ def _substep(models, env_id, g, f64):
     cnt, body, data = eng.contacts()
     torch.cuda.synchronize()
     out = q2.cpu().numpy(), dq2.cpu().numpy(), cnt.cpu().numpy(), body.cpu().numpy(), data.cpu().numpy()
-    assert eng.launch_count >= 3 and "static:" in eng.kernel_name
+    assert eng.launch_count >= 3 and ("static:" in eng.kernel_name or "loop:" in eng.kernel_name)
     eng.close()
     return out
 

@@ -13,6 +13,7 @@ from dart_env_b200.envs import make
 env_id, n = sys.argv[1], int(sys.argv[2])
 env = make(env_id, num_envs=n, output="torch", seed=1, batched=True)
 eng = env.engine
+if os.environ.get("SWEEP_PGS"): eng.set_lcp(1, int(os.environ["SWEEP_PGS"]))
 dev = eng.device
 obs = env.reset()
 gen = torch.Generator(device=dev); gen.manual_seed(1234)
@@ -26,7 +27,7 @@ e0.record()
 for i in range(K): eng.step(acts[i %% 16], env._obs, env._rew, env._done, True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print("%%-20s n=%%7d block=%%4s  %%8.1f us/step  %%.3e env-steps/s" %% (env_id, n, os.environ.get("DARTB_BLOCK", "auto"), ms * 1e3, n / (ms * 1e-3)))
+print("%%-20s n=%%7d block=%%4s lcp=%%s %%8.1f us/step  %%.3e env-steps/s  [%%s]" %% (env_id, n, os.environ.get("DARTB_BLOCK", "auto"), os.environ.get("SWEEP_PGS", "exact"), ms * 1e3, n / (ms * 1e-3), eng.kernel_name))
 ''' % ROOT
 
 cfgs = []
@@ -37,10 +38,19 @@ if mode == "variant":
                           ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
             for b in (("32", "128") if n <= 4096 else ("128",)):
                 cfgs.append((env_id, n, b, v))
+elif mode == "lcp":
+    for v in ("0", "1"):
+        for pgs in ("", "1"):
+            for n in (4096, 65536):
+                cfgs.append(("DartHopper-v1", n, "32" if n == 4096 else "128", v, pgs))
+            cfgs.append(("DartHalfCheetah-v1", 16384, "128", v, pgs))
 else:
     for b in ("32", "64", "128", "256"):
         cfgs.append(("DartHopper-v1", 4096, b, "0"))
-for env_id, n, b, v in cfgs:
+for cfg in cfgs:
+    env_id, n, b, v = cfg[:4]
     env = dict(os.environ, DARTB_BLOCK=b, DARTB_VARIANT=v, DART_ENV_NO_REFERENCE="1")
+    if len(cfg) > 4 and cfg[4]:
+        env["SWEEP_PGS"] = cfg[4]
     r = subprocess.run([sys.executable, "-c", CODE, env_id, str(n)], env=env, capture_output=True, text=True)
     print("variant=%s " % v + (r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)

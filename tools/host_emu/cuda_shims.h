@@ -15,3 +15,4 @@ static inline double __longlong_as_double(long long v) { double f; memcpy(&f, &v
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }

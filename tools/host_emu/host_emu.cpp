@@ -67,6 +67,9 @@ static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, cons
     }
 }
 
+long g_emu_counters[8];
+extern "C" void emu_counters(long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = g_emu_counters[i]; if (reset) g_emu_counters[i] = 0; } }
+
 static std::string g_err;
 
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
