@@ -109,31 +109,41 @@ class ClockSampler:
 # ------------------------------------------------------------------------------ CPU arm
 def cpu_arm(env_id, worlds, steps, warmup, threads, budget_s=60.0):
     """The CPU restatement of the reference path (oracle 'port'), all host threads, auto-reset,
-    same random-action distribution.  Per step a bounded sample of the worlds so the run ends in
-    about `budget_s`."""
+    same random-action distribution.  `steps=None`: choose the step count for about `budget_s`
+    seconds of CPU work over all `worlds`; otherwise keep `steps` and bound the per-step sample of
+    worlds so the run ends in about `budget_s`."""
     from oracle import oracle as orc
     m, spec = build_model(env_id)
-    cal_w = max(threads * 4, 32)
+    cal_w = max(threads * 8, 64)
+    orc.cpu_bench(m, spec.task, cal_w, 5, threads, seed=1)  # page in
     t0 = time.perf_counter()
-    sps, _ = orc.cpu_bench(m, spec.task, cal_w, 20, threads, seed=1)
-    cal = time.perf_counter() - t0
-    rate = cal_w * 20 / max(cal, 1e-6)
-    sample = int(min(worlds, max(threads, rate * budget_s / max(steps + warmup, 1))))
-    if warmup > 0:
-        orc.cpu_bench(m, spec.task, sample, warmup, threads, seed=2)
-    t0 = time.perf_counter()
-    sps, _ = orc.cpu_bench(m, spec.task, sample, steps, threads, seed=3)
-    wall = time.perf_counter() - t0
+    orc.cpu_bench(m, spec.task, cal_w, 40, threads, seed=1)
+    rate = cal_w * 40 / max(time.perf_counter() - t0, 1e-6)
+    if steps is None:
+        # run chunks of 25 steps over all worlds until about budget_s of CPU work has been timed
+        sample, steps, wall = worlds, 0, 0.0
+        while wall < budget_s and steps < 100000:
+            t0 = time.perf_counter()
+            orc.cpu_bench(m, spec.task, sample, 25, threads, seed=3 + steps)
+            wall += time.perf_counter() - t0
+            steps += 25
+    else:
+        sample = int(min(worlds, max(threads, rate * budget_s / max(steps + warmup, 1))))
+        if warmup > 0:
+            orc.cpu_bench(m, spec.task, sample, warmup, threads, seed=2)
+        t0 = time.perf_counter()
+        orc.cpu_bench(m, spec.task, sample, steps, threads, seed=3)
+        wall = time.perf_counter() - t0
     return {"value": sample * steps / wall, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d of %d worlds per step x %d steps (%.1f s of CPU work), fp64 scalar C restatement of "
-                      "pydart2 World.step + task layer, %d pthreads" % (sample, worlds, steps, wall, threads)}, wall
+                      "pydart2 World.step + task layer, %d pthreads" % (sample, worlds, steps, wall, threads)}, wall, steps
 
 
 def run_reference(args, rank, world_size):
     if rank != 0:
         return
     threads = host_threads()
-    cb, wall = cpu_arm(args.env, args.worlds, args.steps, args.warmup, threads)
+    cb, wall, _ = cpu_arm(args.env, args.worlds, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": metric_name(args.env), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -268,7 +278,7 @@ def run_ours(args, rank, local_rank, world_size):
             roof["fp32"] = prof[args.env]["fp32"]
         cb = None
         if world_size >= 1:
-            cb, _ = cpu_arm(args.env, n, 200, 10, host_threads(), budget_s=12.0)
+            cb, _, _ = cpu_arm(args.env, n, None, 5, host_threads(), budget_s=12.0)
         line = {"metric": metric_name(args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
