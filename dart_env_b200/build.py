@@ -1,16 +1,25 @@
-"""Builds libdartb.so in-tree with nvcc for sm_100a (the .so travels to the GPU box)."""
+"""Builds libdartb.so in-tree with nvcc for sm_100a (the .so travels to the GPU box).
+
+Each (topology, precision) instantiation of the kernels is its own translation unit (inst.cu
+compiled with -DINST_*), built in parallel, then linked with the host API (dartb.cu)."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libdartb.so")
-SOURCES = ["dartb.cu"]
-DEPS = ["dartb.cu", "planar_kernels.cuh", "planar_model.h", "lower.h", os.path.join("..", "..", "include", "dartb.h")]
+DEPS = ["dartb.cu", "inst.cu", "kernels.cuh", "planar_kernels.cuh", "planar_loop.cuh", "planar_model.h", "lower.h",
+        os.path.join("..", "..", "include", "dartb.h")]
+INSTANCES = [("hopper", "TopoHopper"), ("walker", "TopoWalker"), ("cheetah", "TopoCheetah"), ("snake", "TopoSnake"),
+             ("loop", None)]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
 def nvcc_path() -> str:
@@ -27,18 +36,33 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return SO
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+def _run(cmd, verbose):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+        sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
         raise RuntimeError("nvcc failed")
+    return res.stdout + res.stderr
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
+    if not force and not is_stale():
+        return SO
+    nvcc = nvcc_path()
+    os.makedirs(OBJ, exist_ok=True)
+    ptxas = ["-Xptxas", "-v"] if verbose else []
+    jobs_list = [(os.path.join(OBJ, "dartb.o"), [nvcc] + ARCH + COMMON + ptxas + ["-c", os.path.join(CSRC, "dartb.cu")])]
+    for name, topo in INSTANCES:
+        for real, sfx in (("float", "f"), ("double", "d")):
+            defs = ["-DINST_REAL=%s" % real, "-DINST_SUFFIX=%s_%s" % (name, sfx)]
+            defs += ["-DINST_LOOP=1"] if topo is None else ["-DINST_TOPO=%s" % topo]
+            obj = os.path.join(OBJ, "inst_%s_%s.o" % (name, sfx))
+            jobs_list.append((obj, [nvcc] + ARCH + COMMON + ptxas + defs + ["-c", os.path.join(CSRC, "inst.cu")]))
+    nj = jobs or min(len(jobs_list), os.cpu_count() or 4)
+    with ThreadPoolExecutor(nj) as ex:
+        logs = list(ex.map(lambda j: _run(j[1] + ["-o", j[0]], verbose), jobs_list))
+    log = _run([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", SO] + [j[0] for j in jobs_list], verbose)
     if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        sys.stderr.write("".join(logs) + log)
     return SO
 
 

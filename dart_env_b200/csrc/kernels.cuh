@@ -1,0 +1,475 @@
+// kernels.cuh — the __global__ kernels of the stepper (templated on topology / precision) and the
+// launcher declarations that let each (topology, precision) pair live in its own translation unit
+// (inst.cu is compiled once per pair, in parallel; see build.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dartb.h"
+#include "planar_kernels.cuh"
+#include "planar_loop.cuh"
+
+// ------------------------------------------------------------------------ kernel arguments
+template <typename R>
+struct StepArgs {
+    int n;
+    R* q;                // [nd][n]
+    R* dq;               // [nd][n]
+    uint32_t* episode;   // [n] reset counter (Philox stream position)
+    int32_t* elapsed;    // [n] env steps since reset (TimeLimit)
+    uint8_t* truncated;  // [n]
+    const float* action; // [n, n_act]
+    float* obs;          // [n, n_obs]
+    float* reward;       // [n]
+    uint8_t* done;       // [n]
+    const uint8_t* mask; // reset mask (k_reset) or null
+    int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
+    uint64_t seed;
+    int64_t world_offset;
+    ContactSink<R> sink;
+};
+
+template <class T, typename R>
+DEVI void write_obs(const PModel<R>& M, const PTask<R>& K, const R (&q)[T::NB], const R (&dq)[T::NB], float* so) {
+    constexpr int NB = T::NB;
+    if (K.obs_mode == DARTB_OBS_HEIGHT_Q2_DQ) {
+        R cs[NB], sn[NB], px[NB], py[NB];
+        fk_positions<T, R>(M, q, cs, sn, px, py);
+        R h = 0;
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if (K.height_body == i) {
+                const R X = px[i] + cs[i] * K.hcx - sn[i] * K.hcy, Y = py[i] + sn[i] * K.hcx + cs[i] * K.hcy;
+                h = K.wy1 * X + K.wy2 * Y + K.wy0;
+            }
+        });
+        so[0] = (float)h;
+    } else {
+        so[0] = (float)q[1];
+    }
+    static_for<2, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; so[i - 1] = (float)q[i]; });
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        R v = dq[i];
+        if (K.dq_clip > 0) v = v > K.dq_clip ? K.dq_clip : (v < -K.dq_clip ? -K.dq_clip : v);
+        so[NB - 1 + i] = (float)v;
+    });
+}
+
+template <class T, typename R>
+DEVI R body_height(const PModel<R>& M, const PTask<R>& K, const R (&q)[T::NB]) {
+    constexpr int NB = T::NB;
+    R cs[NB], sn[NB], px[NB], py[NB];
+    fk_positions<T, R>(M, q, cs, sn, px, py);
+    R h = 0;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (K.height_body == i) {
+            const R X = px[i] + cs[i] * K.hcx - sn[i] * K.hcy, Y = py[i] + sn[i] * K.hcx + cs[i] * K.hcy;
+            h = K.wy1 * X + K.wy2 * Y + K.wy0;
+        }
+    });
+    return h;
+}
+
+// reset_model(): q0 + U(+-noise), dq0 + U(+-noise) in fp32 arithmetic (bit-identical to the oracle)
+template <class T, typename R>
+DEVI void reset_state(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int64_t gw, uint32_t ep, R (&q)[T::NB],
+                      R (&dq)[T::NB]) {
+    constexpr int NB = T::NB;
+    const float noise = (float)K.reset_noise;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const float a = __fmul_rn(reset_uniform(seed, gw, ep, i), noise);
+        const float b = __fmul_rn(reset_uniform(seed, gw, ep, NB + i), noise);
+        q[i] = (R)__fadd_rn((float)M.qinit[i], a);
+        dq[i] = (R)__fadd_rn((float)M.dqinit[i], b);
+    });
+}
+
+// ------------------------------------------------------------------------ env.step() kernel
+template <class T, typename R>
+__global__ void __launch_bounds__(256)
+k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    constexpr int NB = T::NB;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane;                          // first world of this warp
+    const int cnt = min(32, a.n - wb);                // worlds this warp owns (<= 0: idle warp)
+    const bool active = w < a.n;
+    const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
+    float* sw = smem + warp * 32 * stage;
+
+    // coalesced action load -> smem [lane][n_act]
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
+
+    R q[NB], dq[NB], tau[NB], zero[NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+        zero[i] = 0;
+    });
+    // advance(): clamp, scale, scatter (hopper.py:24-32); control cost uses the RAW action
+    R a2 = 0;
+    if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[lane * K.n_act + j]; a2 += v * v; }
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        R t = 0;
+        if (active && K.dof_act[i] >= 0) {
+            R v = (R)sw[lane * K.n_act + K.dof_act[i]];
+            v = v > K.dof_hi[i] ? K.dof_hi[i] : v;
+            v = v < K.dof_lo[i] ? K.dof_lo[i] : v;
+            t = v * K.dof_scale[i];
+        }
+        tau[i] = t;
+    });
+    __syncwarp();
+
+    const R posbefore = q[0];
+    const ContactSink<R>* sink = &a.sink;
+    for (int f = 0; f < K.frame_skip; f++) {
+        const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? sink : nullptr;
+        if (K.fluid_force)
+            substep<T, R, false, true>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w);
+        else
+            substep<T, R, false, false>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, a.lcp_mode, a.pgs_iters, sk, w);
+    }
+    // reward / done (hopper.py:36-65, walker2d.py:22-65, half_cheetah.py:40-77, snake_7link.py:68-87)
+    const R ang = q[2];
+    R r = (q[0] - posbefore) * K.inv_dt_env * K.vel_weight;
+    r += K.alive_bonus;
+    r -= K.ctrl_cost * a2;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (K.limit_pen_dof == i) {
+            R pen = 0;
+            if ((M.qlo[i] - q[i]) > -K.limit_pen_margin) pen += (R)1.5;
+            if ((M.qhi[i] - q[i]) < K.limit_pen_margin) pen += (R)1.5;
+            r -= K.limit_pen_weight * pen;
+        }
+    });
+    r -= K.dev_cost * Num<R>::abs_(ang);
+    bool ok = true;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        // isfinite and |.| < bound in one comparison (NaN / inf fail it)
+        if (i >= 2 && !(Num<R>::abs_(q[i]) < K.state_bound)) ok = false;
+        if (i < 2 && !(Num<R>::abs_(q[i]) < Num<R>::inf())) ok = false;
+        if (!(Num<R>::abs_(dq[i]) < K.state_bound)) ok = false;
+    });
+    if (K.zero_reward_on_blowup && !ok) r = 0;
+    if (K.height_body >= 0) {
+        const R h = body_height<T, R>(M, K, q);
+        ok = ok && (h > K.height_lo) && (h < K.height_hi);
+    }
+    ok = ok && (Num<R>::abs_(ang) < K.ang_max);
+    bool done = !ok;
+    bool trunc = false;
+    if (active && a.max_episode_steps > 0) {
+        const int el = a.elapsed[w] + 1;
+        if (el >= a.max_episode_steps) { trunc = !done; done = true; }
+        a.elapsed[w] = (done && a.auto_reset) ? 0 : el;
+    }
+    if (active && done && a.auto_reset) {
+        const uint32_t ep = a.episode[w];
+        reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+    }
+    // obs (of the reset state for auto-reset worlds: gym/vector/sync_vector_env.py:76-79)
+    if (active) write_obs<T, R>(M, K, q, dq, sw + lane * K.n_obs);
+    __syncwarp();
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (active) {
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            a.q[(size_t)i * a.n + w] = q[i];
+            a.dq[(size_t)i * a.n + w] = dq[i];
+        });
+        a.reward[w] = (float)r;
+        a.done[w] = done ? 1 : 0;
+        if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------ reset kernel
+template <class T, typename R>
+__global__ void __launch_bounds__(256)
+k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    constexpr int NB = T::NB;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane, cnt = min(32, a.n - wb);
+    const bool active = w < a.n;
+    float* sw = smem + warp * 32 * K.n_obs;
+    R q[NB], dq[NB];
+    const bool doit = active && (a.mask == nullptr || a.mask[w]);
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+    });
+    if (doit) {
+        const uint32_t ep = a.episode[w];
+        reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+        a.elapsed[w] = 0;
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            a.q[(size_t)i * a.n + w] = q[i];
+            a.dq[(size_t)i * a.n + w] = dq[i];
+        });
+        if (a.sink.count) a.sink.count[w] = 0;
+    }
+    if (a.obs) {
+        if (active) write_obs<T, R>(M, K, q, dq, sw + lane * K.n_obs);
+        __syncwarp();
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    }
+}
+
+// ------------------------------------------------------------------------ single DART step kernel
+// exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175) with optional ext forces
+template <class T, typename R>
+__global__ void __launch_bounds__(256)
+k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, const R* fext /*[n,nbd,3]*/,
+          int lcp_mode, int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
+    constexpr int NB = T::NB;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    R q[NB], dq[NB], tau[NB], eft[NB], efx[NB], efy[NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        q[i] = qs[(size_t)i * n + w];
+        dq[i] = dqs[(size_t)i * n + w];
+        tau[i] = tau_in ? tau_in[(size_t)w * NB + i] : (R)0;
+        eft[i] = 0; efx[i] = 0; efy[i] = 0;
+    });
+    if (fext) {
+        R cs[NB], sn[NB], px[NB], py[NB];
+        fk_positions<T, R>(M, q, cs, sn, px, py);
+        for (int k = 0; k < M.nbd; k++) {
+            const R* f = fext + ((size_t)w * M.nbd + k) * 3;
+            const R fx = M.e1[0] * f[0] + M.e1[1] * f[1] + M.e1[2] * f[2];
+            const R fy = M.e2[0] * f[0] + M.e2[1] * f[1] + M.e2[2] * f[2];
+            const int g = M.dgroup[k];
+            static_for<0, NB>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                if (g == i) {
+                    const R ox = cs[i] * M.dox[k] - sn[i] * M.doy[k], oy = sn[i] * M.dox[k] + cs[i] * M.doy[k];
+                    eft[i] += ox * fy - oy * fx; efx[i] += fx; efy[i] += fy;
+                }
+            });
+        }
+        substep<T, R, true, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    } else {
+        substep<T, R, false, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    }
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        qs[(size_t)i * n + w] = q[i];
+        dqs[(size_t)i * n + w] = dq[i];
+    });
+}
+
+
+// ======================================================================== loop (generic) variant
+// Same kernels built on planar_loop.cuh: runtime topology, small instruction footprint.
+template <typename R>
+DEVI R body_height_loop(const PModel<R>& M, const PTask<R>& K, const R* q) {
+    R cs[LOOP_MAXB], sn[LOOP_MAXB], px[LOOP_MAXB], py[LOOP_MAXB];
+    fk_positions_loop<R>(M, q, cs, sn, px, py);
+    const int i = K.height_body;
+    const R X = px[i] + cs[i] * K.hcx - sn[i] * K.hcy, Y = py[i] + sn[i] * K.hcx + cs[i] * K.hcy;
+    return K.wy1 * X + K.wy2 * Y + K.wy0;
+}
+template <typename R>
+DEVI void write_obs_loop(const PModel<R>& M, const PTask<R>& K, const R* q, const R* dq, float* so) {
+    const int nb = M.nb;
+    so[0] = (K.obs_mode == DARTB_OBS_HEIGHT_Q2_DQ) ? (float)body_height_loop<R>(M, K, q) : (float)q[1];
+    for (int i = 2; i < nb; i++) so[i - 1] = (float)q[i];
+    for (int i = 0; i < nb; i++) {
+        R v = dq[i];
+        if (K.dq_clip > 0) v = v > K.dq_clip ? K.dq_clip : (v < -K.dq_clip ? -K.dq_clip : v);
+        so[nb - 1 + i] = (float)v;
+    }
+}
+template <typename R>
+DEVI void reset_state_loop(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int64_t gw, uint32_t ep, R* q, R* dq) {
+    const int nb = M.nb;
+    const float noise = (float)K.reset_noise;
+    for (int i = 0; i < nb; i++) {
+        const float a = __fmul_rn(reset_uniform(seed, gw, ep, i), noise);
+        const float b = __fmul_rn(reset_uniform(seed, gw, ep, nb + i), noise);
+        q[i] = (R)__fadd_rn((float)M.qinit[i], a);
+        dq[i] = (R)__fadd_rn((float)M.dqinit[i], b);
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    extern __shared__ float smem[];
+    const int nb = M.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane, cnt = min(32, a.n - wb);
+    const bool active = w < a.n;
+    const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
+    float* sw = smem + warp * 32 * stage;
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
+    R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB];
+    R a2 = 0;
+    if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[lane * K.n_act + j]; a2 += v * v; }
+    for (int i = 0; i < nb; i++) {
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+        R t = 0;
+        if (active && K.dof_act[i] >= 0) {
+            R v = (R)sw[lane * K.n_act + K.dof_act[i]];
+            v = v > K.dof_hi[i] ? K.dof_hi[i] : v;
+            v = v < K.dof_lo[i] ? K.dof_lo[i] : v;
+            t = v * K.dof_scale[i];
+        }
+        tau[i] = t;
+    }
+    __syncwarp();
+    const R posbefore = q[0];
+    for (int f = 0; f < K.frame_skip; f++) {
+        const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? &a.sink : nullptr;
+        substep_loop<R>(M, q, dq, tau, false, tau, tau, tau, K.fluid_force != 0, K.fluid_offset, K.fluid_coef, a.lcp_mode,
+                        a.pgs_iters, sk, w);
+    }
+    const R ang = q[2];
+    R r = (q[0] - posbefore) * K.inv_dt_env * K.vel_weight;
+    r += K.alive_bonus;
+    r -= K.ctrl_cost * a2;
+    if (K.limit_pen_dof >= 0) {
+        const int i = K.limit_pen_dof;
+        R pen = 0;
+        if ((M.qlo[i] - q[i]) > -K.limit_pen_margin) pen += (R)1.5;
+        if ((M.qhi[i] - q[i]) < K.limit_pen_margin) pen += (R)1.5;
+        r -= K.limit_pen_weight * pen;
+    }
+    r -= K.dev_cost * Num<R>::abs_(ang);
+    bool ok = true;
+    for (int i = 0; i < nb; i++) {
+        if (i >= 2 && !(Num<R>::abs_(q[i]) < K.state_bound)) ok = false;
+        if (i < 2 && !(Num<R>::abs_(q[i]) < Num<R>::inf())) ok = false;
+        if (!(Num<R>::abs_(dq[i]) < K.state_bound)) ok = false;
+    }
+    if (K.zero_reward_on_blowup && !ok) r = 0;
+    if (K.height_body >= 0) {
+        const R h = body_height_loop<R>(M, K, q);
+        ok = ok && (h > K.height_lo) && (h < K.height_hi);
+    }
+    ok = ok && (Num<R>::abs_(ang) < K.ang_max);
+    bool done = !ok, trunc = false;
+    if (active && a.max_episode_steps > 0) {
+        const int el = a.elapsed[w] + 1;
+        if (el >= a.max_episode_steps) { trunc = !done; done = true; }
+        a.elapsed[w] = (done && a.auto_reset) ? 0 : el;
+    }
+    if (active && done && a.auto_reset) {
+        const uint32_t ep = a.episode[w];
+        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+    }
+    if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
+    __syncwarp();
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (active) {
+        for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
+        a.reward[w] = (float)r;
+        a.done[w] = done ? 1 : 0;
+        if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    extern __shared__ float smem[];
+    const int nb = M.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = w - lane, cnt = min(32, a.n - wb);
+    const bool active = w < a.n;
+    float* sw = smem + warp * 32 * K.n_obs;
+    R q[LOOP_MAXB], dq[LOOP_MAXB];
+    const bool doit = active && (a.mask == nullptr || a.mask[w]);
+    for (int i = 0; i < nb; i++) {
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+    }
+    if (doit) {
+        const uint32_t ep = a.episode[w];
+        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        a.episode[w] = ep + 1;
+        a.elapsed[w] = 0;
+        for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
+        if (a.sink.count) a.sink.count[w] = 0;
+    }
+    if (a.obs) {
+        if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
+        __syncwarp();
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in, const R* fext, int lcp_mode,
+               int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
+    const int nb = M.nb;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB], eft[LOOP_MAXB], efx[LOOP_MAXB], efy[LOOP_MAXB];
+    for (int i = 0; i < nb; i++) {
+        q[i] = qs[(size_t)i * n + w];
+        dq[i] = dqs[(size_t)i * n + w];
+        tau[i] = tau_in ? tau_in[(size_t)w * nb + i] : (R)0;
+        eft[i] = 0; efx[i] = 0; efy[i] = 0;
+    }
+    if (fext) {
+        R cs[LOOP_MAXB], sn[LOOP_MAXB], px[LOOP_MAXB], py[LOOP_MAXB];
+        fk_positions_loop<R>(M, q, cs, sn, px, py);
+        for (int k = 0; k < M.nbd; k++) {
+            const R* f = fext + ((size_t)w * M.nbd + k) * 3;
+            const R fx = M.e1[0] * f[0] + M.e1[1] * f[1] + M.e1[2] * f[2];
+            const R fy = M.e2[0] * f[0] + M.e2[1] * f[1] + M.e2[2] * f[2];
+            const int g = M.dgroup[k];
+            const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
+            eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
+        }
+        substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    } else {
+        substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+    }
+    for (int i = 0; i < nb; i++) { qs[(size_t)i * n + w] = q[i]; dqs[(size_t)i * n + w] = dq[i]; }
+}
+
+
+// ------------------------------------------------------------------------ launchers (one set per TU)
+template <typename R>
+struct Launchers {
+    void (*step)(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
+    void (*reset)(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
+    void (*substep)(int grid, int bs, cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, const R* fext,
+                    int lcp_mode, int pgs_iters, const ContactSink<R>& sink);
+};
+#define DARTB_DECLARE_LAUNCHERS(SUFFIX, R) extern const Launchers<R> dartb_launchers_##SUFFIX;
+DARTB_DECLARE_LAUNCHERS(hopper_f, float)
+DARTB_DECLARE_LAUNCHERS(hopper_d, double)
+DARTB_DECLARE_LAUNCHERS(walker_f, float)
+DARTB_DECLARE_LAUNCHERS(walker_d, double)
+DARTB_DECLARE_LAUNCHERS(cheetah_f, float)
+DARTB_DECLARE_LAUNCHERS(cheetah_d, double)
+DARTB_DECLARE_LAUNCHERS(snake_f, float)
+DARTB_DECLARE_LAUNCHERS(snake_d, double)
+DARTB_DECLARE_LAUNCHERS(loop_f, float)
+DARTB_DECLARE_LAUNCHERS(loop_d, double)

@@ -42,6 +42,13 @@ extern long g_emu_counters[8];  // [0] exact LCP calls [1] solved by lcp_small<4
 #define EMU_COUNT(i, v) ((void)0)
 #endif
 
+// max of v over the lanes of this warp that are currently executing this code
+#ifdef DARTB_HOST_EMU
+static inline int warp_max_active(int v) { return v; }
+#else
+DEVI int warp_max_active(int v) { return __reduce_max_sync(__activemask(), v); }
+#endif
+
 // ------------------------------------------------------------------------ static loops
 template <int I, int N, class F>
 DEVI void static_for(F&& f) {
@@ -470,13 +477,109 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     return true;
 }
 
-// exact LCP: register fast paths for n <= 4 / n <= 8, Dantzig in thread-local memory beyond
+// The same block-principal-pivoting iteration for any n <= NR, as loops over thread-local arrays
+// (used above the register sizes; still ~n^3/6 + 3n^2 MACs per iteration and 2-3 iterations per
+// stage, against one fresh factorisation per pivot in the Dantzig loop).
+template <typename R, int NR>
+DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, const R* hi_in, const int* fidx) {
+    R L[NR * NR], y[NR], lo[NR], hi[NR];
+    uint64_t st = 0;
+    for (int i = 0; i < n; i++) {
+        lo[i] = lo_in[i]; hi[i] = hi_in[i];
+        x[i] = 0;
+        uint64_t s = 0;
+        if (!(A[i * n + i] > Num<R>::inert()) || fidx[i] >= 0) s = 3;
+        st |= s << (2 * i);
+    }
+    for (int stage = 0; stage < 2; stage++) {
+        if (stage == 1) {
+            bool any = false;
+            for (int i = 0; i < n; i++)
+                if (fidx[i] >= 0 && A[i * n + i] > Num<R>::inert()) {
+                    const R h = Num<R>::abs_(hi[i] * x[fidx[i]]);
+                    hi[i] = h; lo[i] = -h;
+                    st &= ~((uint64_t)3 << (2 * i));
+                    if (h == 0) st |= (uint64_t)3 << (2 * i); else any = true;
+                }
+            if (!any) break;
+        }
+        int best = n + 1, tries = 3;
+        bool done = false;
+        for (int it = 0; it < 12 * n + 12 && !done; it++) {
+            for (int i = 0; i < n; i++) {
+                const unsigned si = (unsigned)(st >> (2 * i)) & 3u;
+                if (si != 0) x[i] = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
+            }
+            for (int i = 0; i < n; i++) {
+                if (((st >> (2 * i)) & 3u) != 0) { y[i] = 0; continue; }
+                R r = b[i];
+                for (int j = 0; j < n; j++) if (((st >> (2 * j)) & 3u) != 0) r -= A[i * n + j] * x[j];
+                y[i] = r;
+            }
+            for (int i = 0; i < n; i++) {
+                const bool fr = ((st >> (2 * i)) & 3u) == 0;
+                for (int j = 0; j <= i; j++) {
+                    const bool fj = ((st >> (2 * j)) & 3u) == 0;
+                    R s = (fr && fj) ? A[i * n + j] : (i == j ? (R)1 : (R)0);
+                    for (int k = 0; k < j; k++) s -= L[i * NR + k] * L[j * NR + k];
+                    if (i == j) { if (!(s > 0)) return false; L[i * NR + i] = (R)1 / Num<R>::sqrt_(s); }
+                    else L[i * NR + j] = s * L[j * NR + j];
+                }
+            }
+            for (int i = 0; i < n; i++) {
+                R s = y[i];
+                for (int k = 0; k < i; k++) s -= L[i * NR + k] * y[k];
+                y[i] = s * L[i * NR + i];
+            }
+            for (int i = n - 1; i >= 0; i--) {
+                R s = y[i];
+                for (int k = i + 1; k < n; k++) s -= L[k * NR + i] * y[k];
+                y[i] = s * L[i * NR + i];
+            }
+            for (int i = 0; i < n; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
+            uint64_t nst = st;
+            int nbad = 0, last = -1;
+            for (int i = 0; i < n; i++) {
+                const unsigned si = (unsigned)(st >> (2 * i)) & 3u;
+                if (si == 3) continue;
+                const uint64_t clr = ~((uint64_t)3 << (2 * i));
+                if (si == 0) {
+                    if (x[i] < lo[i]) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)1 << (2 * i)); }
+                    else if (x[i] > hi[i]) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)2 << (2 * i)); }
+                } else {
+                    R w = -b[i];
+                    for (int j = 0; j < n; j++) w += A[i * n + j] * x[j];
+                    if (((si == 1 && w < 0) || (si == 2 && w > 0)) && lo[i] < hi[i]) { nbad++; last = i; nst = nst & clr; }
+                }
+            }
+            EMU_COUNT(4, 1);
+            if (nbad == 0) { done = true; break; }
+            if (nbad < best) { best = nbad; tries = 3; st = nst; }
+            else if (tries > 0) { tries--; st = nst; }
+            else { const uint64_t m2 = (uint64_t)3 << (2 * last); st = (st & ~m2) | (nst & m2); }
+        }
+        if (!done) return false;
+    }
+    return true;
+}
+
+// exact LCP dispatch.  The size class is chosen per WARP (max n over the lanes that have rows), so
+// a warp executes ONE code path instead of one per distinct n: register block pivoting for
+// n <= 4 / 6 / 8, the thread-local block pivoting above that, Dantzig only if pivoting fails.
 template <typename R, int NR>
 DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int* fidx) {
+    const int nmax = warp_max_active(n);
     bool ok = false;
     EMU_COUNT(0, 1);
-    if (n <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
-    else if (n <= 8 && NR > 4) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(2, 1); }
+    if (nmax <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
+    else if (nmax <= 6 && NR > 4) { ok = lcp_small<R, 6>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
+    else if (NR > 6) {
+        if (n <= 8) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(2, 1); }
+    }
+    if (!ok) {
+        ok = lcp_bpp_local<R, NR>(n, A, x, b, lo, hi, fidx);
+        if (ok) EMU_COUNT(5, 1);
+    }
     if (!ok) { EMU_COUNT(3, 1); lcp_dantzig<R, NR>(n, A, x, b, lo, hi, fidx); }
 }
 
@@ -665,10 +768,17 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 const R ccx = px[b] + cs[b] * M.scx[s] - sn[b] * M.scy[s], ccy = py[b] + sn[b] * M.scx[s] + cs[b] * M.scy[s];
                 const R adx = cs[b] * M.sdx[s] - sn[b] * M.sdy[s], ady = sn[b] * M.sdx[s] + cs[b] * M.sdy[s];
                 const R hl = M.shalf[s], rad = M.srad[s];
-                R lx, ly, ddx, ddy;
-                closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy,
-                                        M.ghx, M.ghy, lx, ly, ddx, ddy);
-                const R d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+                // broad phase: capsule AABB (segment box inflated by r) against the ground box AABB.
+                // Disjoint by more than 10 um => distance - r > 0 => no contact (exact reject); only
+                // overlapping pairs pay for the ODE closest-point walk.
+                const R ex_ = hl * Num<R>::abs_(adx) + rad + (R)1e-5, ey_ = hl * Num<R>::abs_(ady) + rad + (R)1e-5;
+                const bool near_ = Num<R>::abs_(ccx - M.gcx) <= M.ghx + ex_ && Num<R>::abs_(ccy - M.gcy) <= M.ghy + ey_;
+                R lx = 0, ly = 0, ddx = 0, ddy = 0, d = INF;
+                if (near_) {
+                    closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy,
+                                            M.ghx, M.ghy, lx, ly, ddx, ddy);
+                    d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+                }
                 if (!(d > rad)) {
                     R nx, ny, depth, Px, Py;
                     if (!(d < Num<R>::mindist())) {  // ODE dCollideCapsuleBox: pl == pb up to mindist

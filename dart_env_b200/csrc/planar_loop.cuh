@@ -171,10 +171,14 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
             const R ccx = px[b] + cb * M.scx[s] - sb * M.scy[s], ccy = py[b] + sb * M.scx[s] + cb * M.scy[s];
             const R adx = cb * M.sdx[s] - sb * M.sdy[s], ady = sb * M.sdx[s] + cb * M.sdy[s];
             const R hl = M.shalf[s], rad = M.srad[s];
-            R lx, ly, ddx, ddy;
-            closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy, M.ghx,
-                                    M.ghy, lx, ly, ddx, ddy);
-            const R d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+            const R ex_ = hl * Num<R>::abs_(adx) + rad + (R)1e-5, ey_ = hl * Num<R>::abs_(ady) + rad + (R)1e-5;
+            const bool near_ = Num<R>::abs_(ccx - M.gcx) <= M.ghx + ex_ && Num<R>::abs_(ccy - M.gcy) <= M.ghy + ey_;
+            R lx = 0, ly = 0, ddx = 0, ddy = 0, d = INF;
+            if (near_) {  // broad-phase AABB reject (see planar_kernels.cuh)
+                closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy, M.ghx,
+                                        M.ghy, lx, ly, ddx, ddy);
+                d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+            }
             if (!(d > rad) && n + 2 <= NR) {
                 R nx, ny, depth, Px, Py;
                 if (!(d < Num<R>::mindist())) {

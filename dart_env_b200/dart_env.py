@@ -108,6 +108,9 @@ class DartEnv:
         self._h_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory()
         self._h_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
         self._h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        self._n_obs = np.empty((n, self.obs_dim), dtype=np.float32)
+        self._n_rew = np.empty((n,), dtype=np.float32)
+        self._n_done = np.empty((n,), dtype=np.uint8)
 
     @property
     def max_episode_steps(self):
@@ -171,11 +174,22 @@ class DartEnv:
             act = a.reshape(self.num_envs, self.act_dim).to(torch.float32).contiguous()
             self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)
         else:
-            self._h_act.copy_(torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim)))
-            self._act.copy_(self._h_act, non_blocking=True)
-            self.engine.step(self._act, self._obs, self._rew, self._done, self.auto_reset)
+            # host path: one library call does pinned H2D, the launch, one D2H and the sync
+            act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
+            self.engine.step_host(act, self._n_obs, self._n_rew, self._n_done, self.auto_reset)
+            if self.batched:
+                infos = {}
+                if self._max_episode_steps:
+                    infos["TimeLimit.truncated"] = self.engine.truncated().cpu().numpy().astype(bool)
+                return self._n_obs.copy(), self._n_rew.astype(np.float64), self._n_done.astype(np.bool_), infos
+            info = {}
+            done = bool(self._n_done[0])
+            if self._max_episode_steps and done:
+                info["TimeLimit.truncated"] = bool(self.engine.truncated()[0].item())
+            return self._n_obs[0].astype(np.float64), float(self._n_rew[0]), done, info
         if self.batched and self.output == "torch":
             return self._obs, self._rew, self._done.bool(), {}
+        # a CUDA-tensor action with numpy output: copy the results out
         self._h_obs.copy_(self._obs, non_blocking=True)
         self._h_rew.copy_(self._rew, non_blocking=True)
         self._h_done.copy_(self._done, non_blocking=True)
@@ -188,10 +202,8 @@ class DartEnv:
                     infos)
         info = {}
         done = bool(self._h_done[0].item())
-        if self._max_episode_steps:
-            tr = bool(self.engine.truncated()[0].item())
-            if done:
-                info["TimeLimit.truncated"] = tr
+        if self._max_episode_steps and done:
+            info["TimeLimit.truncated"] = bool(self.engine.truncated()[0].item())
         return self._h_obs.numpy()[0].astype(np.float64), float(self._h_rew[0].item()), done, info
 
     def _out_obs(self, obs):

@@ -111,6 +111,18 @@ class Engine:
         capi.check(self.L.dartb_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done), int(auto_reset),
                                      self._stream()))
 
+    def step_host(self, action, obs, reward, done, auto_reset: bool = True):
+        """env.step() on host (numpy) buffers: float32 [n,n_act] in; float32 [n,n_obs], float32 [n],
+        uint8 [n] out.  H2D, launch, D2H and the sync happen inside the library (pinned staging)."""
+        import numpy as np
+        for a, shape, dt in ((action, (self.n, self.n_act), np.float32), (obs, (self.n, self.n_obs), np.float32),
+                             (reward, (self.n,), np.float32), (done, (self.n,), np.uint8)):
+            if a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("expected C-contiguous %s array of shape %s" % (dt.__name__, shape))
+        capi.check(self.L.dartb_step_host(self.h, C.c_void_p(action.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                          C.c_void_p(reward.ctypes.data), C.c_void_p(done.ctypes.data), int(auto_reset),
+                                          self._stream()))
+
     def substep(self, tau: Optional[torch.Tensor], fext: Optional[torch.Tensor] = None):
         dt = (tau if tau is not None else fext)
         dt = torch.float32 if dt is None else dt.dtype

@@ -137,6 +137,13 @@ int dartb_get_state_f64(dartb_handle_t h, double* d_q, double* d_dq, void* strea
 int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_reward,
                uint8_t* d_done, int32_t auto_reset, void* stream);
 
+/* The same env.step() for HOST buffers (numpy arrays of the reference-facing wrapper): copies the
+ * actions through pinned staging to the device, launches, copies obs | reward | done back with one
+ * transfer and synchronises.  h_* are ordinary host pointers.  This is the end-to-end call a
+ * DartEnv user makes per step (bench.py "e2e"). */
+int dartb_step_host(dartb_handle_t h, const float* h_action, float* h_obs, float* h_reward,
+                    uint8_t* h_done, int32_t auto_reset, void* stream);
+
 /* Exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175): one DART time step
  * with generalized forces d_tau [n, nd]; optional external world-frame forces at body
  * origins d_fext [n, n_bodies, 3] (bn.add_ext_force, snake_7link.py:47), may be NULL. */

@@ -76,3 +76,42 @@ def test_reset_noise_generator_matches_oracle():
     L = emu.lib()
     for seed, w, ep, i in [(0, 0, 0, 0), (1234, 1017, 3, 7), (2 ** 40 + 5, 2 ** 33, 9, 17)]:
         assert L.emu_reset_uniform(seed, w, ep, i) == orc.reset_uniform(seed, w, ep, i)
+
+
+def _random_contact_lcp(rng, nc, nl, mu=1.0, rank_def=False):
+    """LCP with the kernel's row layout: (normal, tangent) per contact, then limit rows."""
+    n = 2 * nc + nl
+    G = rng.normal(size=(n, n + 2 if not rank_def else max(2, n - 2)))
+    A = G @ G.T
+    A += np.diag(np.diag(A)) * 1e-5 + 1e-9 * np.eye(n)   # the CFM the kernel applies
+    b = rng.normal(size=n) * 2
+    lo, hi, fi = np.zeros(n), np.full(n, np.inf), -np.ones(n, dtype=np.int32)
+    for c in range(nc):
+        lo[2 * c + 1], hi[2 * c + 1], fi[2 * c + 1] = -mu, mu, 2 * c
+    for k in range(nl):
+        if rng.random() < 0.5:
+            lo[2 * nc + k], hi[2 * nc + k] = -np.inf, 0.0
+    return A, b, lo, hi, fi
+
+
+@pytest.mark.parametrize("mode,maxn", [(0, 20), (4, 4), (5, 6), (1, 8), (2, 20), (3, 20)])
+def test_kernel_lcp_solvers_equal_oracle_dantzig(mode, maxn):
+    """Every LCP code path of the kernel (register block pivoting <4>/<6>/<8>, thread-local block
+    pivoting, Dantzig, and the dispatch) returns the oracle's Dantzig solution: the two-stage
+    boxed LCP has a unique solution for positive-definite A."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(100 + mode)
+    worst = 0.0
+    for trial in range(300):
+        nc = int(rng.integers(0, 5))
+        nl = int(rng.integers(0 if nc else 1, 4))
+        if 2 * nc + nl > maxn:
+            continue
+        A, b, lo, hi, fi = _random_contact_lcp(rng, nc, nl, mu=float(rng.choice([1.0, 0.5, 0.05])), rank_def=(trial % 7 == 0))
+        xr, *_rest = orc.solve_lcp_dantzig(A, b, lo.copy(), hi.copy(), fi)
+        x, rc = emu.lcp(A, b, lo, hi, fi, mode=mode, f64=True)
+        assert rc == 0
+        # compare the physically meaningful quantity A x (x itself is not unique when A is singular up to CFM)
+        err = np.abs(A @ (x - xr)).max() / (1 + np.abs(A @ xr).max())
+        worst = max(worst, err)
+    assert worst < 1e-6, worst

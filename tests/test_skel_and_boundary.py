@@ -153,9 +153,14 @@ def test_lowering_rejects_non_planar_and_unknown(models):
     m.bodies[4].axis = np.array([0.0, 1.0, 0.0])  # shin joint leaves the plane
     with pytest.raises(capi.DartbError, match="non-planar"):
         capi.describe(m, SPECS["DartHopper-v1"].task)
+    # a planar skeleton without a dedicated instantiation runs on the topology-generic loop kernel
     m = copy.deepcopy(models["DartHopper-v1"])
     m.shapes = m.shapes[:3]
-    with pytest.raises(capi.DartbError, match="no kernel instantiation"):
+    assert capi.describe(m, SPECS["DartHopper-v1"].task) == "planar-xy/loop:generic/f32 nd=6 max_contacts=3"
+    # weld to world / unsupported statics are still rejected loudly
+    m = copy.deepcopy(models["DartHopper-v1"])
+    m.ground = m.ground + m.ground
+    with pytest.raises(capi.DartbError, match="more than one static"):
         capi.describe(m, SPECS["DartHopper-v1"].task)
 
 

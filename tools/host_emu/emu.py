@@ -43,3 +43,17 @@ def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_
     if rc:
         raise RuntimeError(L.emu_last_error().decode())
     return q2, dq2, cnt, body, data
+
+
+def lcp(A, b, lo, hi, findex, mode=0, f64=True):
+    """Kernel-source LCP solvers on the CPU (mode: 0 dispatch, 1 small<8>, 2 bpp_local, 3 dantzig,
+    4 small<4>, 5 small<6>).  Returns (x, failed)."""
+    L = lib()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    b, lo, hi = (np.ascontiguousarray(v, dtype=np.float64) for v in (b, lo, hi))
+    fi = np.ascontiguousarray(findex, dtype=np.int32)
+    x = np.zeros(n)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = L.emu_lcp(int(f64), n, dp(A), dp(b), dp(lo), dp(hi), fi.ctypes.data_as(C.POINTER(C.c_int32)), int(mode), dp(x))
+    return x, rc

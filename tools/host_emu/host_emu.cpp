@@ -102,3 +102,31 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
 extern "C" float emu_reset_uniform(uint64_t seed, int64_t world, uint32_t episode, int i) {
     return reset_uniform(seed, world, episode, i);
 }
+
+// standalone LCP entry for tests: mode 0 = lcp_exact dispatch, 1 = lcp_small<8>, 2 = lcp_bpp_local,
+// 3 = lcp_dantzig, 4 = lcp_small<4>, 5 = lcp_small<6>.  Returns 0 ok, 1 solver reported failure.
+template <typename R>
+static int run_lcp(int n, const double* A, const double* b, const double* lo, const double* hi, const int* fidx, int mode,
+                   double* x) {
+    constexpr int NR = 28;
+    R a[NR * NR], bb[NR], l[NR], h[NR], xx[NR];
+    int fi[NR];
+    for (int i = 0; i < n; i++) {
+        bb[i] = (R)b[i]; l[i] = (R)lo[i]; h[i] = (R)hi[i]; fi[i] = fidx[i]; xx[i] = 0;
+        for (int j = 0; j < n; j++) a[i * n + j] = (R)A[i * n + j];
+    }
+    bool ok = true;
+    if (mode == 0) lcp_exact<R, NR>(n, a, xx, bb, l, h, fi);
+    else if (mode == 1) ok = lcp_small<R, 8>(n, a, xx, bb, l, h, fi);
+    else if (mode == 2) ok = lcp_bpp_local<R, NR>(n, a, xx, bb, l, h, fi);
+    else if (mode == 3) lcp_dantzig<R, NR>(n, a, xx, bb, l, h, fi);
+    else if (mode == 4) ok = lcp_small<R, 4>(n, a, xx, bb, l, h, fi);
+    else if (mode == 5) ok = lcp_small<R, 6>(n, a, xx, bb, l, h, fi);
+    for (int i = 0; i < n; i++) x[i] = (double)xx[i];
+    return ok ? 0 : 1;
+}
+extern "C" int emu_lcp(int f64, int n, const double* A, const double* b, const double* lo, const double* hi, const int* fidx,
+                       int mode, double* x) {
+    if (n > 28) return 2;
+    return f64 ? run_lcp<double>(n, A, b, lo, hi, fidx, mode, x) : run_lcp<float>(n, A, b, lo, hi, fidx, mode, x);
+}
