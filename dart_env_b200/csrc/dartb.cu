@@ -127,7 +127,7 @@ static int block_for(int n) {
     // dominant); several warps per SM share the instruction stream.  DARTB_BLOCK overrides (experiments).
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("DARTB_BLOCK"); forced = e ? atoi(e) : 0; }
-    if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+    if (forced >= 32 && forced <= 128 && forced % 32 == 0) return forced;
     return n <= 148 * 32 * 4 ? 32 : (n <= 148 * 64 * 8 ? 64 : 128);
 }
 

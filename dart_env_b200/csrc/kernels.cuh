@@ -89,7 +89,7 @@ DEVI void reset_state(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int6
 
 // ------------------------------------------------------------------------ env.step() kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -196,7 +196,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
 
 // ------------------------------------------------------------------------ reset kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -234,7 +234,7 @@ k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K,
 // ------------------------------------------------------------------------ single DART step kernel
 // exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175) with optional ext forces
 template <class T, typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, const R* fext /*[n,nbd,3]*/,
           int lcp_mode, int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
     constexpr int NB = T::NB;
@@ -310,7 +310,7 @@ DEVI void reset_state_loop(const PModel<R>& M, const PTask<R>& K, uint64_t seed,
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     extern __shared__ float smem[];
     const int nb = M.nb;
@@ -391,7 +391,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     extern __shared__ float smem[];
     const int nb = M.nb;
@@ -422,7 +422,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 1)
 k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in, const R* fext, int lcp_mode,
                int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
     const int nb = M.nb;

@@ -118,6 +118,7 @@ template <typename R> struct Num;
 template <> struct Num<float> {
     static DEVI void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
     static DEVI float sqrt_(float x) { return sqrtf(x); }
+    static DEVI float rsqrt_(float x) { return rsqrtf(x); }   // MUFU.RSQ, 2 ulp: inner solves of the LCP only
     static DEVI float abs_(float x) { return fabsf(x); }
     static DEVI float inf() { return __int_as_float(0x7f800000); }
     static DEVI float inert() { return 1e-14f; }
@@ -126,6 +127,7 @@ template <> struct Num<float> {
 template <> struct Num<double> {
     static DEVI void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
     static DEVI double sqrt_(double x) { return sqrt(x); }
+    static DEVI double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static DEVI double abs_(double x) { return fabs(x); }
     static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static DEVI double inert() { return 1e-14; }
@@ -359,10 +361,14 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         x[i] = 0;
 #pragma unroll
         for (int j = 0; j < NM; j++) A[i][j] = (on && j < n) ? Ag[i * n + j] : (i == j ? (R)1 : (R)0);
+        // initial active set = the solution of the decoupled (diagonal) problem: a unilateral row is
+        // free iff its own b asks for an impulse of the admissible sign; usually already correct, so
+        // the first pivoting iteration only verifies it.
         unsigned s = 0;
         if (!on || !(A[i][i] > Num<R>::inert())) s = 3;           // padding / inert row
         else if (fi[i] >= 0) s = 3;                                 // friction rows wait for stage 2
-        else if (lo[i] > -INF && hi[i] == INF) s = 0;               // start free (sticking / active guess)
+        else if (lo[i] == 0 && hi[i] == INF) s = b[i] > 0 ? 0u : 1u;
+        else if (hi[i] == 0 && lo[i] == -INF) s = b[i] < 0 ? 0u : 2u;
         st |= s << (2 * i);
     }
     bool ok = true;
@@ -418,7 +424,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
                     R s = (fr && fj) ? A[i][j] : (i == j ? (R)1 : (R)0);
 #pragma unroll
                     for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-                    if (i == j) { if (!(s > 0)) { pd = false; s = 1; } L[i][i] = (R)1 / Num<R>::sqrt_(s); }
+                    if (i == j) { if (!(s > 0)) { pd = false; s = 1; } L[i][i] = Num<R>::rsqrt_(s); }
                     else L[i][j] = s * L[j][j];
                 }
             }
@@ -471,7 +477,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         if (!done) { ok = false; }
         if (!ok) break;
     }
-    if (!ok) return false;
+    if (!ok) { EMU_COUNT(6, 1); return false; }
 #pragma unroll
     for (int i = 0; i < NM; i++) if (i < n) xg[i] = x[i];
     return true;
@@ -489,6 +495,8 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
         x[i] = 0;
         uint64_t s = 0;
         if (!(A[i * n + i] > Num<R>::inert()) || fidx[i] >= 0) s = 3;
+        else if (lo[i] == 0 && hi[i] == Num<R>::inf()) s = b[i] > 0 ? 0 : 1;
+        else if (hi[i] == 0 && lo[i] == -Num<R>::inf()) s = b[i] < 0 ? 0 : 2;
         st |= s << (2 * i);
     }
     for (int stage = 0; stage < 2; stage++) {
@@ -522,7 +530,7 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
                     const bool fj = ((st >> (2 * j)) & 3u) == 0;
                     R s = (fr && fj) ? A[i * n + j] : (i == j ? (R)1 : (R)0);
                     for (int k = 0; k < j; k++) s -= L[i * NR + k] * L[j * NR + k];
-                    if (i == j) { if (!(s > 0)) return false; L[i * NR + i] = (R)1 / Num<R>::sqrt_(s); }
+                    if (i == j) { if (!(s > 0)) return false; L[i * NR + i] = Num<R>::rsqrt_(s); }
                     else L[i * NR + j] = s * L[j * NR + j];
                 }
             }
@@ -871,10 +879,13 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 }
             });
         }
-        // M^-1 J^T, one impulse pass per row (DART: applyUnitImpulse + getVelocityChange)
+        // M^-1 J^T, one impulse pass per row (DART: applyUnitImpulse + getVelocityChange), and row r of
+        // A = J M^-1 J^T formed right away from the pass result still in registers (lower triangle,
+        // mirrored: A is symmetric)
         R MJ[NR * NB];
+        R A[NR * NR], x[NR];
         for (int r = 0; r < n; r++) {
-            R rh[NB], ur[NB], apt[NB], apx[NB], apy[NB];
+            R rh[NB], ur[NB], apt[NB], apx[NB], apy[NB], ddr[NB];
             static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; rh[i] = Jr[r * NB + i]; apt[i] = 0; apx[i] = 0; apy[i] = 0; });
             static_rfor<NB>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
@@ -900,17 +911,16 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 const R dd = Ei[i] * (ur[i] - (V0[i] * p0 + V1[i] * p1 + V2[i] * p2));
                 if constexpr (T::jtype(i) == PM_REV) { a0[i] = p0 + M.sgn[i] * dd; a1[i] = p1; a2[i] = p2; }
                 else { a0[i] = p0; a1[i] = p1 + uwx[i] * dd; a2[i] = p2 + uwy[i] * dd; }
+                ddr[i] = dd;
                 MJ[r * NB + i] = dd;
             });
-        }
-        R A[NR * NR], x[NR];
-        for (int r = 0; r < n; r++)
-            for (int s = 0; s < n; s++) {
+            for (int s = 0; s <= r; s++) {
                 R v = 0;
-#pragma unroll
-                for (int j = 0; j < NB; j++) v += Jr[s * NB + j] * MJ[r * NB + j];
+                static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; v += Jr[s * NB + j] * ddr[j]; });
                 A[r * n + s] = v;
+                A[s * n + r] = v;
             }
+        }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
         if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
         else lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx);

@@ -265,6 +265,7 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
             }
         }
         R MJ[NR * MB];
+        R A[NR * NR], x[NR];
 #pragma unroll 1
         for (int r = 0; r < n; r++) {
             R ur[MB], a0[MB], a1[MB], a2[MB];
@@ -293,14 +294,13 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
                 a0[i] = p0 + s0[i] * dd; a1[i] = p1 + s1[i] * dd; a2[i] = p2 + s2[i] * dd;
                 MJ[r * MB + i] = dd;
             }
-        }
-        R A[NR * NR], x[NR];
-        for (int r = 0; r < n; r++)
-            for (int s = 0; s < n; s++) {
+            for (int s = 0; s <= r; s++) {  // row r of A = J M^-1 J^T (lower triangle, mirrored)
                 R v = 0;
                 for (int j = 0; j < nb; j++) v += Jr[s * MB + j] * MJ[r * MB + j];
                 A[r * n + s] = v;
+                A[s * n + r] = v;
             }
+        }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
         if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
         else lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx);

@@ -16,3 +16,4 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
