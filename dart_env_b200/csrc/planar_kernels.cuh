@@ -123,6 +123,7 @@ template <> struct Num<float> {
     static DEVI float inf() { return __int_as_float(0x7f800000); }
     static DEVI float inert() { return 1e-14f; }
     static DEVI float mindist() { return 1e-6f; }   // ODE dCollideCapsuleBox, dSINGLE build
+    static DEVI float lcp_tol() { return 7.6e-6f; }   // 64 eps: complementarity tests of the pivoting LCP
 };
 template <> struct Num<double> {
     static DEVI void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
@@ -132,6 +133,7 @@ template <> struct Num<double> {
     static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static DEVI double inert() { return 1e-14; }
     static DEVI double mindist() { return 1e-15; }  // ODE dCollideCapsuleBox, dDOUBLE build
+    static DEVI double lcp_tol() { return 1.4e-14; }
 };
 
 // DART constants (ContactConstraint.cpp / JointLimitConstraint.cpp), see oracle/dart_oracle.c
@@ -224,6 +226,7 @@ DEVI bool chol_solve_sub(int n, const R* A, const int* idx, int nC, const R* rhs
         for (int b = 0; b <= a; b++) {
             R s = A[ia * n + idx[b]];
             for (int k = 0; k < b; k++) s -= L[a * NR + k] * L[b * NR + k];
+            EMU_COUNT(7, b);
             if (a == b) {
                 if (!(s > 0)) return false;
                 L[a * NR + a] = Num<R>::sqrt_(s);
@@ -372,6 +375,12 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         st |= s << (2 * i);
     }
     bool ok = true;
+    // rounding-aware feasibility tests: |A_ij x_j| <= sqrt(A_ii) sqrt(A_jj) |x_j| (A is PSD), so
+    // sqrt(A_ii) * sum_j sqrt(A_jj)|x_j| bounds the magnitude of the terms of w_i.  Without the
+    // tolerance a degenerate row (x at its bound AND w = 0) flips between sets forever in fp32.
+    R sd[NM];
+#pragma unroll
+    for (int i = 0; i < NM; i++) sd[i] = Num<R>::sqrt_(A[i][i]);
 #pragma unroll 1
     for (int stage = 0; stage < 2; stage++) {
         if (stage == 1) {
@@ -393,7 +402,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         int best = NM + 1, tries = 3;
         bool done = false;
 #pragma unroll 1
-        for (int it = 0; it < 12 * NM && !done; it++) {
+        for (int it = 0; it < 6 + 3 * NM && !done; it++) {
             // masked system: free rows keep A, bound rows become identity with rhs = bound value
             R L[NM][NM], y[NM];
 #pragma unroll
@@ -445,22 +454,27 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
             }
 #pragma unroll
             for (int i = 0; i < NM; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
-            // infeasibilities
+            // infeasibilities (with rounding tolerances)
             unsigned bad = 0;  // bit i set: row i must change set
             int nbad = 0;
             unsigned nst = st;
+            R xs = 0, S = 0;
+#pragma unroll
+            for (int i = 0; i < NM; i++) { const R ax = Num<R>::abs_(x[i]); xs = ax > xs ? ax : xs; S += sd[i] * ax; }
+            const R tx = Num<R>::lcp_tol() * xs;
 #pragma unroll
             for (int i = 0; i < NM; i++) {
                 const unsigned si = (st >> (2 * i)) & 3u;
                 if (si == 3) continue;
                 if (si == 0) {
-                    if (x[i] < lo[i]) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
-                    else if (x[i] > hi[i]) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
+                    if (x[i] < lo[i] - tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
+                    else if (x[i] > hi[i] + tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
                 } else {
                     R w = -b[i];
 #pragma unroll
                     for (int j = 0; j < NM; j++) w += A[i][j] * x[j];
-                    if ((si == 1 && w < 0) || (si == 2 && w > 0)) {
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
+                    if ((si == 1 && w < -tw) || (si == 2 && w > tw)) {
                         if (lo[i] < hi[i]) { bad |= 1u << i; nbad++; nst = nst & ~(3u << (2 * i)); }
                     }
                 }
@@ -489,6 +503,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
 template <typename R, int NR>
 DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, const R* hi_in, const int* fidx) {
     R L[NR * NR], y[NR], lo[NR], hi[NR];
+    int idx[NR];
     uint64_t st = 0;
     for (int i = 0; i < n; i++) {
         lo[i] = lo_in[i]; hi[i] = hi_in[i];
@@ -513,51 +528,62 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
         }
         int best = n + 1, tries = 3;
         bool done = false;
-        for (int it = 0; it < 12 * n + 12 && !done; it++) {
+        for (int it = 0; it < 3 * n + 6 && !done; it++) {
+            // compact list of free rows; bound rows take their bound value
+            int nF = 0;
             for (int i = 0; i < n; i++) {
                 const unsigned si = (unsigned)(st >> (2 * i)) & 3u;
-                if (si != 0) x[i] = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
+                if (si == 0) idx[nF++] = i;
+                else x[i] = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
             }
-            for (int i = 0; i < n; i++) {
-                if (((st >> (2 * i)) & 3u) != 0) { y[i] = 0; continue; }
-                R r = b[i];
-                for (int j = 0; j < n; j++) if (((st >> (2 * j)) & 3u) != 0) r -= A[i * n + j] * x[j];
-                y[i] = r;
-            }
-            for (int i = 0; i < n; i++) {
-                const bool fr = ((st >> (2 * i)) & 3u) == 0;
-                for (int j = 0; j <= i; j++) {
-                    const bool fj = ((st >> (2 * j)) & 3u) == 0;
-                    R s = (fr && fj) ? A[i * n + j] : (i == j ? (R)1 : (R)0);
-                    for (int k = 0; k < j; k++) s -= L[i * NR + k] * L[j * NR + k];
-                    if (i == j) { if (!(s > 0)) return false; L[i * NR + i] = Num<R>::rsqrt_(s); }
-                    else L[i * NR + j] = s * L[j * NR + j];
+            // rhs_F = b_F - A_FB x_B ; Cholesky of A_FF ; solve
+            for (int a = 0; a < nF; a++) {
+                const int ia = idx[a];
+                R r = b[ia];
+                for (int j = 0; j < n; j++) if (((st >> (2 * j)) & 3u) != 0) r -= A[ia * n + j] * x[j];
+                y[a] = r;
+                for (int c = 0; c <= a; c++) {
+                    R s = A[ia * n + idx[c]];
+#pragma unroll 4
+                    for (int k = 0; k < c; k++) s -= L[a * NR + k] * L[c * NR + k];
+                    EMU_COUNT(7, c);
+                    if (a == c) { if (!(s > 0)) return false; L[a * NR + a] = Num<R>::rsqrt_(s); }
+                    else L[a * NR + c] = s * L[c * NR + c];
                 }
             }
-            for (int i = 0; i < n; i++) {
-                R s = y[i];
-                for (int k = 0; k < i; k++) s -= L[i * NR + k] * y[k];
-                y[i] = s * L[i * NR + i];
+            for (int a = 0; a < nF; a++) {
+                R s = y[a];
+#pragma unroll 4
+                for (int k = 0; k < a; k++) s -= L[a * NR + k] * y[k];
+                y[a] = s * L[a * NR + a];
             }
-            for (int i = n - 1; i >= 0; i--) {
-                R s = y[i];
-                for (int k = i + 1; k < n; k++) s -= L[k * NR + i] * y[k];
-                y[i] = s * L[i * NR + i];
+            for (int a = nF - 1; a >= 0; a--) {
+                R s = y[a];
+#pragma unroll 4
+                for (int k = a + 1; k < nF; k++) s -= L[k * NR + a] * y[k];
+                y[a] = s * L[a * NR + a];
             }
-            for (int i = 0; i < n; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
+            EMU_COUNT(7, nF * nF);
+            for (int a = 0; a < nF; a++) x[idx[a]] = y[a];
             uint64_t nst = st;
             int nbad = 0, last = -1;
+            R xs = 0, S = 0;
+            for (int i = 0; i < n; i++) { const R ax = Num<R>::abs_(x[i]); xs = ax > xs ? ax : xs; S += Num<R>::sqrt_(A[i * n + i]) * ax; }
+            const R tx = Num<R>::lcp_tol() * xs;
             for (int i = 0; i < n; i++) {
                 const unsigned si = (unsigned)(st >> (2 * i)) & 3u;
                 if (si == 3) continue;
                 const uint64_t clr = ~((uint64_t)3 << (2 * i));
                 if (si == 0) {
-                    if (x[i] < lo[i]) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)1 << (2 * i)); }
-                    else if (x[i] > hi[i]) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)2 << (2 * i)); }
+                    if (x[i] < lo[i] - tx) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)1 << (2 * i)); }
+                    else if (x[i] > hi[i] + tx) { nbad++; last = i; nst = (nst & clr) | ((uint64_t)2 << (2 * i)); }
                 } else {
                     R w = -b[i];
+#pragma unroll 4
                     for (int j = 0; j < n; j++) w += A[i * n + j] * x[j];
-                    if (((si == 1 && w < 0) || (si == 2 && w > 0)) && lo[i] < hi[i]) { nbad++; last = i; nst = nst & clr; }
+                    EMU_COUNT(7, n);
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + Num<R>::sqrt_(A[i * n + i]) * S);
+                    if (((si == 1 && w < -tw) || (si == 2 && w > tw)) && lo[i] < hi[i]) { nbad++; last = i; nst = nst & clr; }
                 }
             }
             EMU_COUNT(4, 1);
