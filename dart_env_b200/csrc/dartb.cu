@@ -325,6 +325,7 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
 
 int dartb_reset(dartb_handle_t e, const uint8_t* d_mask, float* d_obs, void* stream) {
     if (!e) return fail("null handle");
+    if (e->task.n_obs == 0 && d_obs) return fail("physics-only handle has no observation layout");
     DeviceGuard g(e->device);
     return e->f64 ? launch_reset<double>(e, d_mask, d_obs, (cudaStream_t)stream)
                   : launch_reset<float>(e, d_mask, d_obs, (cudaStream_t)stream);
@@ -355,6 +356,7 @@ int dartb_step(dartb_handle_t e, const float* d_action, float* d_obs, float* d_r
                int32_t auto_reset, void* stream) {
     if (!e) return fail("null handle");
     if (!d_action || !d_obs || !d_reward || !d_done) return fail("null device pointer");
+    if (e->task.n_obs == 0) return fail("physics-only handle: no task layer configured (use dartb_substep)");
     DeviceGuard g(e->device);
     return e->f64 ? launch_step<double>(e, d_action, d_obs, d_reward, d_done, auto_reset, (cudaStream_t)stream)
                   : launch_step<float>(e, d_action, d_obs, d_reward, d_done, auto_reset, (cudaStream_t)stream);
@@ -364,6 +366,7 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
                     int32_t auto_reset, void* stream) {
     if (!e) return fail("null handle");
     if (!h_action || !h_obs || !h_reward || !h_done) return fail("null host pointer");
+    if (e->task.n_obs == 0) return fail("physics-only handle: no task layer configured (use dartb_substep)");
     DeviceGuard g(e->device);
     const int n = e->n, na = e->task.n_act, no = e->task.n_obs;
     // layout of the staging block (floats): [action n*na | obs n*no | reward n | done n bytes]

@@ -281,7 +281,14 @@ static std::string lower_model(const dartb_model_t& dm, const dartb_task_t& dt_,
     out.max_contacts = ns > 0 ? ns : 1;
     out.signature = sig;
 
-    // ---- task
+    // ---- task (n_obs == 0: physics-only handle, dartb_substep / state access only)
+    if (dt_.n_obs == 0 && dt_.n_act == 0) {
+        for (int i = 0; i < PM_MAXB; i++) t.dof_act[i] = -1;
+        t.frame_skip = dt_.frame_skip > 0 ? dt_.frame_skip : 1;
+        t.height_body = -1; t.limit_pen_dof = -1;
+        t.inv_dt_env = 1.0 / (dm.dt * t.frame_skip);
+        return "";
+    }
     if (dt_.n_act > PM_MAXA) return "too many actuators";
     t.frame_skip = dt_.frame_skip; t.n_act = dt_.n_act; t.n_obs = dt_.n_obs;
     for (int i = 0; i < PM_MAXB; i++) t.dof_act[i] = -1;

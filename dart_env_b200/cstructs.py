@@ -122,6 +122,12 @@ class Task:
     def n_act(self) -> int:
         return len(self.act_dof)
 
+    @staticmethod
+    def physics_only(frame_skip: int = 1) -> "Task":
+        """No fused task layer: the handle serves dartb_substep / state access only (the env's
+        obs / reward / done are then computed by the host class, like the reference does)."""
+        return Task(frame_skip=frame_skip, act_dof=[], act_scale=[], n_obs=0, reset_noise=0.0)
+
 
 def pack_task(t: Task) -> CTask:
     if t.n_act > MAX_ACT:

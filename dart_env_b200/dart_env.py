@@ -54,9 +54,12 @@ class DartEnv:
         if friction_all is not None:
             for b in self.model.bodies:
                 b.friction_coeff = float(friction_all)
+        # task=None: physics-only handle; the subclass computes obs / reward / done on the host side
+        # (torch ops over the batched state), calling do_simulation() like the reference classes do
+        self.fused = task is not None
         if task is None:
-            raise ValueError("a Task (dart_env_b200.cstructs.Task) describing obs/reward/done is required")
-        if task.frame_skip != frame_skip or task.n_obs != observation_size:
+            task = Task.physics_only(frame_skip)
+        elif task.frame_skip != frame_skip or task.n_obs != observation_size:
             raise ValueError("task does not match frame_skip / observation_size")
         self.task = task
         self.frame_skip = frame_skip
@@ -143,8 +146,15 @@ class DartEnv:
         return self.model.dt * self.frame_skip
 
     def reset(self):
+        if not self.fused:
+            return self._out_obs(self.reset_model())
         obs = self.engine.reset(None, self._obs)
         return self._out_obs(obs)
+
+    def reset_model(self):
+        """Reset the robot degrees of freedom (qpos and qvel).  Implemented by host-side task classes
+        (dart_env.py:125-130 of the reference); fused envs reset inside the kernel."""
+        raise NotImplementedError
 
     def set_state(self, qpos, qvel):
         q = torch.as_tensor(np.asarray(qpos, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
@@ -164,12 +174,16 @@ class DartEnv:
 
     def do_simulation(self, tau, n_frames):
         """dart_env.py:158-175: n_frames x {set_forces(tau); world.step()} (perturbation off)."""
-        t = torch.as_tensor(np.asarray(tau, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
-        t = t.contiguous()
+        if isinstance(tau, torch.Tensor):
+            t = tau.reshape(self.num_envs, -1).to(self.engine.device).contiguous()
+        else:
+            t = torch.as_tensor(np.asarray(tau, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device).contiguous()
         for _ in range(n_frames):
             self.engine.substep(t)
 
     def step(self, a):
+        if not self.fused:
+            raise NotImplementedError("host-side task classes implement step()")
         if isinstance(a, torch.Tensor) and a.is_cuda:
             act = a.reshape(self.num_envs, self.act_dim).to(torch.float32).contiguous()
             self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)

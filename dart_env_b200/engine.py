@@ -94,6 +94,11 @@ class Engine:
 
     # --- stepping
     def reset(self, mask: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.n_obs == 0:  # physics-only handle: world.reset() only
+            if mask is not None:
+                self._chk(mask, (self.n,), torch.uint8)
+            capi.check(self.L.dartb_reset(self.h, _ptr(mask), None, self._stream()))
+            return None
         if obs is None:
             obs = torch.empty((self.n, self.n_obs), dtype=torch.float32, device=self.device)
         self._chk(obs, (self.n, self.n_obs), torch.float32)

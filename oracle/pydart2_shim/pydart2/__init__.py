@@ -119,6 +119,7 @@ class _Skeleton(object):
             self.bodynodes, self.joints, self.ndofs = [], [], 0
             return
         self.bodynodes = [_BodyNode(self, i) for i in range(model.n_bodies)]
+        self.name_to_body = {b.name: b for b in self.bodynodes}
         self.joints = [_Joint(self, i) for i in range(model.n_bodies)]
         self.ndofs = model.n_dofs
 

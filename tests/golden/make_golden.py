@@ -34,7 +34,37 @@ REF_CLASSES = {
     "DartHalfCheetah-v1": ("gym.envs.dart.half_cheetah", "DartHalfCheetahEnv"),
     "DartSnake7Link-v1": ("gym.envs.dart.snake_7link", "DartSnake7LinkEnv"),
 }
+# SURVEY 8f.1 contact-free envs (host-side task layer in dart_env_b200/envs_contact_free.py)
+REF_CLASSES_CF = {
+    "DartCartPole-v1": ("gym.envs.dart.cart_pole", "DartCartPoleEnv", "cartpole.skel", 0.02),
+    "DartCartPoleSwingUp-v1": ("gym.envs.dart.cartpole_swingup", "DartCartPoleSwingUpEnv", "cartpole_swingup.skel", 0.01),
+    "DartDoubleInvertedPendulumEnv-v1": ("gym.envs.dart.inverted_double_pendulum", "DartDoubleInvertedPendulumEnv",
+                                         "inverted_double_pendulum.skel", 0.01),
+}
 MAXC = 8
+
+
+def contact_free_rollouts(env_id, n_steps, seed):
+    import importlib
+    mod, cls, skel, dt = REF_CLASSES_CF[env_id]
+    env = getattr(importlib.import_module(mod), cls)()
+    env.seed(seed)
+    rng = np.random.RandomState(seed)
+    rec = {k: [] for k in ("q", "dq", "action", "obs", "reward", "done", "q2", "dq2")}
+    for scale in (1.0, 0.3, 0.05):
+        env.reset()
+        for t in range(n_steps):
+            a = rng.uniform(-1, 1, 1) * scale
+            s0 = env.state_vector()
+            ob, r, d, _ = env.step(a)
+            s1 = env.state_vector()
+            nd = len(s0) // 2
+            rec["q"].append(s0[:nd]); rec["dq"].append(s0[nd:]); rec["action"].append(a)
+            rec["obs"].append(ob); rec["reward"].append(r); rec["done"].append(d)
+            rec["q2"].append(s1[:nd]); rec["dq2"].append(s1[nd:])
+            if d:
+                env.reset()
+    return {"step_" + k: np.array(v) for k, v in rec.items()}
 
 
 def build_model(env_id):
@@ -187,5 +217,18 @@ def main():
               "max lcp rows", int(sub["sub_lcp_rows"].max()), os.path.getsize(path) // 1024, "KiB")
 
 
+def main_contact_free():
+    outdir = os.path.dirname(os.path.abspath(__file__))
+    for env_id in REF_CLASSES_CF:
+        roll = contact_free_rollouts(env_id, n_steps=80, seed=5)
+        name = {"DartCartPole-v1": "cartpole", "DartCartPoleSwingUp-v1": "cartpole_swingup",
+                "DartDoubleInvertedPendulumEnv-v1": "double_pendulum"}[env_id]
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, env_id=env_id, **roll)
+        print(env_id, "->", path, "steps", len(roll["step_q"]), "done", int(roll["step_done"].sum()), os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--contact-free" not in sys.argv:
+        main()
+    main_contact_free()

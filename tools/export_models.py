@@ -13,7 +13,11 @@ sys.path.insert(0, ROOT)
 from dart_env_b200.skel import find_asset, parse_skel  # noqa: E402
 from dart_env_b200.tasks import SPECS  # noqa: E402
 
-for spec in SPECS.values():
+EXTRA = ["cartpole.skel", "cartpole_swingup.skel", "inverted_double_pendulum.skel"]
+for skel in [spec.skel for spec in SPECS.values()] + EXTRA:
+    class spec:  # noqa: N801
+        pass
+    spec.skel = skel
     src = find_asset(spec.skel)
     m = parse_skel(src)  # file's own <time_step>; the env passes dt at load time
     out = os.path.join(ROOT, "dart_env_b200", "assets", spec.skel[:-5] + ".model.json")
