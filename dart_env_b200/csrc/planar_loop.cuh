@@ -127,7 +127,7 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
         }
         u += -M.kspring[i] * (q[i] - M.rest[i] + dt * dq[i]) - M.damping[i] * dq[i];
         D += dt * M.damping[i] + dt * dt * M.kspring[i];
-        const R di = (R)1 / D;
+        const R di = Num<R>::rcp_(D);
         U0[i] = u0; U1[i] = u1; U2[i] = u2; Di[i] = di; uu[i] = u;
         if (par >= 0) {
             const R g = u * di;
@@ -182,7 +182,8 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
             if (!(d > rad) && n + 2 <= NR) {
                 R nx, ny, depth, Px, Py;
                 if (!(d < Num<R>::mindist())) {
-                    nx = ddx / d; ny = ddy / d;
+                    const R id = Num<R>::rcp_(d);
+                    nx = ddx * id; ny = ddy * id;
                     depth = rad - d;
                     const R k = (R)0.5 * (-rad - d);
                     Px = lx + nx * k; Py = ly + ny * k;
@@ -253,7 +254,7 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
                 v0 = hx * a + hy * b; v1 = ma * a + mb * b; v2 = mb * a + mc * b;
                 D = a * v1 + b * v2;
             }
-            const R di = (R)1 / D;
+            const R di = Num<R>::rcp_(D);
             V0[i] = v0; V1[i] = v1; V2[i] = v2; Ei[i] = di;
             if (par >= 0) {
                 const R P00 = J - v0 * v0 * di, P01 = hx - v0 * v1 * di, P02 = hy - v0 * v2 * di;
