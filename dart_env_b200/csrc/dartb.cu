@@ -60,6 +60,7 @@ struct dartb_engine {
     void* q = nullptr; void* dq = nullptr;
     void* scratch = nullptr;                  // [n * max(nd, nbd*3)] of Real for tau / fext conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
+    uint64_t* hint = nullptr;                 // LCP warm-start sets, see planar_kernels.cuh::substep
     int32_t* ccount = nullptr; int32_t* cbody = nullptr; float* cdata = nullptr;
     int lcp_mode = 0, pgs_iters = 30, max_episode_steps = 0;
     int variant_request = -1;                 // -1 auto (DARTB_VARIANT env or static if available), 0, 1
@@ -97,7 +98,7 @@ static int lower_into(dartb_engine* e) {
     if (res.m.ns > LOOP_MAXS || res.m.nb > LOOP_MAXB) return fail("model too large for the planar kernels");
     static int forced_variant = -1;
     if (forced_variant < 0) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : 0; }
-    if (topo < 0 || e->variant_request == 1 || (e->variant_request < 0 && forced_variant == 1)) e->variant = 1;
+    if (topo < 0 || res.m.any_coulomb || e->variant_request == 1 || (e->variant_request < 0 && forced_variant == 1)) e->variant = 1;
     else e->variant = 0;
     e->topo = topo;
     e->md = res.m; e->td = res.t;
@@ -137,6 +138,7 @@ static StepArgs<R> make_args(dartb_engine* e) {
     std::memset(&a, 0, sizeof a);
     a.n = e->n; a.q = (R*)e->q; a.dq = (R*)e->dq; a.episode = e->episode; a.elapsed = e->elapsed;
     a.truncated = e->truncated;
+    a.hint = e->hint;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset;
     a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; a.sink.maxc = e->max_contacts;
@@ -230,6 +232,8 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
     auto A = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) err = cudaMemset(*p, 0, bytes); } };
     A(&e->q, rs * n * e->nd); A(&e->dq, rs * n * e->nd); A(&e->scratch, rs * sc);
     A((void**)&e->episode, 4 * (size_t)n); A((void**)&e->elapsed, 4 * (size_t)n); A((void**)&e->truncated, (size_t)n);
+    A((void**)&e->hint, 8 * (size_t)n);
+    if (err == cudaSuccess) err = cudaMemset(e->hint, 0xFF, 8 * (size_t)n);
     A((void**)&e->ccount, 4 * (size_t)n); A((void**)&e->cbody, 4 * (size_t)n * e->max_contacts);
     A((void**)&e->cdata, 4 * (size_t)n * e->max_contacts * 10);
     if (err != cudaSuccess) { dartb_destroy(e); return fail(std::string("cudaMalloc: ") + cudaGetErrorString(err)); }
@@ -255,6 +259,7 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
 template <typename S>
 static int set_state_impl(dartb_handle_t e, const S* q, const S* dq, cudaStream_t st) {
     const int tot = e->n * e->nd, bs = 256, grid = (tot + bs - 1) / bs;
+    CK(cudaMemsetAsync(e->hint, 0xFF, 8 * (size_t)e->n, st));  // a new state invalidates the LCP warm start
     if (e->f64) {
         if (q) { k_to_soa<S, double><<<grid, bs, 0, st>>>(e->n, e->nd, q, (double*)e->q); e->launches++; }
         if (dq) { k_to_soa<S, double><<<grid, bs, 0, st>>>(e->n, e->nd, dq, (double*)e->dq); e->launches++; }
@@ -293,7 +298,7 @@ int dartb_destroy(dartb_handle_t e) {
     if (!e) return 0;
     DeviceGuard g(e->device);
     cudaFree(e->q); cudaFree(e->dq); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
-    cudaFree(e->truncated); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
+    cudaFree(e->truncated); cudaFree(e->hint); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->d_stage) cudaFree(e->d_stage);
     delete e;

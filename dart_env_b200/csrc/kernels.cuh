@@ -18,6 +18,7 @@ struct StepArgs {
     uint32_t* episode;   // [n] reset counter (Philox stream position)
     int32_t* elapsed;    // [n] env steps since reset (TimeLimit)
     uint8_t* truncated;  // [n]
+    uint64_t* hint;      // [n] LCP active-set warm start (2 bits per constraint slot), all ones = none
     const float* action; // [n, n_act]
     float* obs;          // [n, n_obs]
     float* reward;       // [n]
@@ -130,12 +131,13 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
 
     const R posbefore = q[0];
     const ContactSink<R>* sink = &a.sink;
+    uint64_t hint = active ? a.hint[w] : ~(uint64_t)0;
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? sink : nullptr;
         if (K.fluid_force)
-            substep<T, R, false, true>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w);
+            substep<T, R, false, true>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w, hint);
         else
-            substep<T, R, false, false>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, a.lcp_mode, a.pgs_iters, sk, w);
+            substep<T, R, false, false>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, a.lcp_mode, a.pgs_iters, sk, w, hint);
     }
     // reward / done (hopper.py:36-65, walker2d.py:22-65, half_cheetah.py:40-77, snake_7link.py:68-87)
     const R ang = q[2];
@@ -177,7 +179,9 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
         const uint32_t ep = a.episode[w];
         reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
         a.episode[w] = ep + 1;
+        hint = ~(uint64_t)0;
     }
+    if (active) a.hint[w] = hint;
     // obs (of the reset state for auto-reset worlds: gym/vector/sync_vector_env.py:76-79)
     if (active) write_obs<T, R>(M, K, q, dq, sw + lane * K.n_obs);
     __syncwarp();
@@ -217,6 +221,7 @@ k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K,
         reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
         a.episode[w] = ep + 1;
         a.elapsed[w] = 0;
+        a.hint[w] = ~(uint64_t)0;
         static_for<0, NB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             a.q[(size_t)i * a.n + w] = q[i];
@@ -264,9 +269,11 @@ k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* ta
                 }
             });
         }
-        substep<T, R, true, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        uint64_t hint = ~(uint64_t)0;  // the literal World.step() drop-in is stateless
+        substep<T, R, true, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, hint);
     } else {
-        substep<T, R, false, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        uint64_t hint = ~(uint64_t)0;
+        substep<T, R, false, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, hint);
     }
     static_for<0, NB>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
@@ -411,6 +418,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
         reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
         a.episode[w] = ep + 1;
         a.elapsed[w] = 0;
+        a.hint[w] = ~(uint64_t)0;
         for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
         if (a.sink.count) a.sink.count[w] = 0;
     }

@@ -176,7 +176,8 @@ static std::string lower_model(const dartb_model_t& dm, const dartb_task_t& dt_,
         m.qinit[gi] = b.q_init;
         m.dqinit[gi] = b.dq_init;
         m.orig_body[gi] = r;
-        if (b.coulomb != 0.0) return "joint Coulomb friction is not implemented (SURVEY 8f.1)";
+        m.coulomb[gi] = b.coulomb;
+        if (b.coulomb != 0.0) m.any_coulomb = 1;
         V3 o = Tw[r].p - P0[gi];
         m.ox[gi] = dot(e1, o);
         m.oy[gi] = dot(e2, o);
@@ -339,6 +340,7 @@ static void convert(const PModel<double>& a, PModel<R>& b) {
         b.mass[i] = (R)a.mass[i]; b.cx[i] = (R)a.cx[i]; b.cy[i] = (R)a.cy[i]; b.izz[i] = (R)a.izz[i];
         b.ox[i] = (R)a.ox[i]; b.oy[i] = (R)a.oy[i];
         b.damping[i] = (R)a.damping[i]; b.kspring[i] = (R)a.kspring[i]; b.rest[i] = (R)a.rest[i];
+        b.coulomb[i] = (R)a.coulomb[i];
         b.qlo[i] = (R)a.qlo[i]; b.qhi[i] = (R)a.qhi[i]; b.limited[i] = a.limited[i];
         b.qinit[i] = (R)a.qinit[i]; b.dqinit[i] = (R)a.dqinit[i];
         b.fnx[i] = (R)a.fnx[i]; b.fny[i] = (R)a.fny[i]; b.orig_body[i] = a.orig_body[i];
@@ -350,6 +352,7 @@ static void convert(const PModel<double>& a, PModel<R>& b) {
         b.scx[i] = (R)a.scx[i]; b.scy[i] = (R)a.scy[i]; b.sdx[i] = (R)a.sdx[i]; b.sdy[i] = (R)a.sdy[i];
         b.shalf[i] = (R)a.shalf[i]; b.srad[i] = (R)a.srad[i]; b.smu[i] = (R)a.smu[i];
     }
+    b.any_coulomb = a.any_coulomb;
     b.has_ground = a.has_ground;
     b.gcx = (R)a.gcx; b.gcy = (R)a.gcy; b.ghx = (R)a.ghx; b.ghy = (R)a.ghy;
     b.gupx = (R)a.gupx; b.gupy = (R)a.gupy; b.ghup = (R)a.ghup;

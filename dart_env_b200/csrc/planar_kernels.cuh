@@ -359,7 +359,8 @@ DEVI void lcp_dantzig(int n, const R* A, R* x, const R* b, R* lo, R* hi, const i
 // Dantzig returns; ncu showed the Dantzig loop (thread-local arrays, 3-5 active lanes) to be 50% of
 // the kernel's instructions.  Returns false if it did not converge (caller falls back to Dantzig).
 template <typename R, int NM>
-DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg) {
+DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg,
+                    const uint8_t* hin = nullptr, uint8_t* sout = nullptr) {
     R A[NM][NM], b[NM], lo[NM], hi[NM], x[NM], mu[NM];
     int fi[NM];
     unsigned st = 0;  // 2 bits per row: 0 free, 1 at lo, 2 at hi, 3 permanently bound at x = 0
@@ -375,11 +376,16 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         // initial active set = the solution of the decoupled (diagonal) problem: a unilateral row is
         // free iff its own b asks for an impulse of the admissible sign; usually already correct, so
         // the first pivoting iteration only verifies it.
+        // (`hin[i]`, the set the row ended in at the previous DART step, is used for the FRICTION rows
+        // in stage 2 only: stick/slide persists between steps, while for the unilateral rows the
+        // decoupled guess above measured better than the previous step's set under random actions)
+        const unsigned h = (hin && on) ? hin[i] : 3u;
         unsigned s = 0;
         if (!on || !(A[i][i] > Num<R>::inert())) s = 3;           // padding / inert row
         else if (fi[i] >= 0) s = 3;                                 // friction rows wait for stage 2
         else if (lo[i] == 0 && hi[i] == INF) s = b[i] > 0 ? 0u : 1u;
         else if (hi[i] == 0 && lo[i] == -INF) s = b[i] < 0 ? 0u : 2u;
+        (void)h;
         st |= s << (2 * i);
     }
     bool ok = true;
@@ -402,7 +408,9 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
                     const R h = Num<R>::abs_(mu[i] * xn);
                     hi[i] = h; lo[i] = -h;
                     st &= ~(3u << (2 * i));
-                    if (h == 0) st |= 3u << (2 * i); else any = true;   // free at first
+                    const unsigned hh = hin ? hin[i] : 3u;
+                    if (h == 0) st |= 3u << (2 * i);
+                    else { any = true; if (hh < 3u) st |= hh << (2 * i); }   // hinted set, else free (sticking)
                 }
             }
             if (!any) break;
@@ -501,7 +509,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     }
     if (!ok) { EMU_COUNT(6, 1); return false; }
 #pragma unroll
-    for (int i = 0; i < NM; i++) if (i < n) xg[i] = x[i];
+    for (int i = 0; i < NM; i++) if (i < n) { xg[i] = x[i]; if (sout) sout[i] = (uint8_t)((st >> (2 * i)) & 3u); }
     return true;
 }
 
@@ -609,16 +617,18 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
 // a warp executes ONE code path instead of one per distinct n: register block pivoting for
 // n <= 4 / 6 / 8, the thread-local block pivoting above that, Dantzig only if pivoting fails.
 template <typename R, int NR>
-DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int* fidx) {
+DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int* fidx, const uint8_t* hin = nullptr,
+                    uint8_t* sout = nullptr) {
     const int nmax = warp_max_active(n);
     bool ok = false;
     EMU_COUNT(0, 1);
-    if (nmax <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
-    else if (nmax <= 6 && NR > 4) { ok = lcp_small<R, 6>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(1, 1); }
+    if (nmax <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
+    else if (nmax <= 6 && NR > 4) { ok = lcp_small<R, 6>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (NR > 6) {
-        if (n <= 8) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx); if (ok) EMU_COUNT(2, 1); }
+        if (n <= 8) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(2, 1); }
     }
     if (!ok) {
+        if (sout) for (int i = 0; i < n; i++) sout[i] = 3;
         ok = lcp_bpp_local<R, NR>(n, A, x, b, lo, hi, fidx);
         if (ok) EMU_COUNT(5, 1);
     }
@@ -684,7 +694,9 @@ DEVI void fk_positions(const PModel<R>& M, const R (&q)[T::NB], R (&cs)[T::NB], 
 template <class T, typename R, bool FEXT, bool FLUID>
 DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&tau)[T::NB], const R (&eft)[T::NB],
                   const R (&efx)[T::NB], const R (&efy)[T::NB], R fluid_offset, R fluid_coef, int lcp_mode,
-                  int pgs_iters, const ContactSink<R>* sink, int world) {
+                  int pgs_iters, const ContactSink<R>* sink, int world, uint64_t& hint) {
+    // `hint`: 2 bits per constraint SLOT (contact s -> slots 2s, 2s+1; limit of dof i -> 2*NS + i):
+    // the set (0 free, 1 at lo, 2 at hi, 3 unknown) the slot's row ended in at the previous step.
     constexpr int NB = T::NB, NS = T::NS, NR = T::NR;
     const R dt = M.dt;
     // ---------------- K1: forward kinematics, velocities, partial accelerations
@@ -798,6 +810,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
     int n = 0, nc = 0;
     R Jr[NR * NB], bb[NR], lo[NR], hi[NR];
     int fidx[NR];
+    uint8_t rslot[NR];
     R cpx[T::NSA], cpy[T::NSA], cnx[T::NSA], cny[T::NSA], cdep[T::NSA];
     int crow[T::NSA], cshape[T::NSA];
     const R INF = Num<R>::inf();
@@ -855,9 +868,9 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                     R bounce = depth;
                     if (bounce < 0) bounce = 0;
                     else { bounce *= inv_dt * (R)DK_CONTACT_ERP; if (bounce > (R)DK_CONTACT_MAX_ERV) bounce = (R)DK_CONTACT_MAX_ERV; }
-                    bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1;
+                    bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1; rslot[r0] = 2 * s;
                     n = r0 + 1;
-                    if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; n = r0 + 2; }
+                    if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; rslot[r0 + 1] = 2 * s + 1; n = r0 + 2; }
                     cpx[nc] = Px; cpy[nc] = Py; cnx[nc] = nx; cny[nc] = ny; cdep[nc] = depth; crow[nc] = r0 | (fric ? 0x100 : 0);
                     cshape[nc] = s;
                     nc++;
@@ -878,11 +891,13 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 bb[n] = -dq[i];
                 if (act < 0) { lo[n] = 0; hi[n] = INF; } else { lo[n] = -INF; hi[n] = 0; }
                 fidx[n] = -1;
+                rslot[n] = 2 * NS + i;
                 n++;
             }
         }
     });
 
+    uint64_t new_hint = ~(uint64_t)0;
     if (n > 0) {
         // plain (non-implicit) articulated inertia for the impulse passes
         R V0[NB], V1[NB], V2[NB], Ei[NB];
@@ -958,7 +973,13 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
         }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
         if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
-        else lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx);
+        else {
+            uint8_t hrow[NR], srow[NR];
+            for (int r = 0; r < n; r++) hrow[r] = (uint8_t)((hint >> (2 * rslot[r])) & 3u);
+            lcp_exact<R, NR>(n, A, x, bb, lo, hi, fidx, hrow, srow);
+            for (int r = 0; r < n; r++)
+                new_hint = (new_hint & ~((uint64_t)3 << (2 * rslot[r]))) | ((uint64_t)srow[r] << (2 * rslot[r]));
+        }
         // ---------------- K7: apply impulses
         for (int r = 0; r < n; r++) {
             const R xr = x[r];
@@ -987,6 +1008,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
         if (sink->body)
             for (int c = 0; c < sink->maxc; c++) sink->body[(size_t)world * sink->maxc + c] = c < nc ? M.sorig[cshape[c]] : -1;
     }
+    hint = new_hint;
     // ---------------- integrate positions
     static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; q[i] += dt * dq[i]; });
 }

@@ -17,7 +17,7 @@
 
 #define LOOP_MAXB PM_MAXB
 #define LOOP_MAXS PM_MAXS
-#define LOOP_MAXR (2 * PM_MAXS + 8) /* rows: (n,t) per capsule + up to 8 simultaneously active limits */
+#define LOOP_MAXR 32 /* rows: (n,t) per capsule + active limits + Coulomb-friction rows (<= 32: 64-bit state word) */
 
 template <typename R>
 DEVI void fk_positions_loop(const PModel<R>& M, const R* q, R* cs, R* sn, R* px, R* py) {
@@ -231,6 +231,19 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
             for (int j = 0; j < nb; j++) Jr[n * MB + j] = (j == i) ? (R)1 : (R)0;
             bb[n] = -dq[i];
             if (act < 0) { lo[n] = 0; hi[n] = INF; } else { lo[n] = -INF; hi[n] = 0; }
+            fidx[n] = -1;
+            n++;
+        }
+    }
+    if (M.any_coulomb) {
+        // JointCoulombFrictionConstraint rows (after the limit rows, like DART): b = -dq, |x| <= friction*dt
+#pragma unroll 1
+        for (int i = 0; i < nb; i++) {
+            if (M.coulomb[i] == 0 || dq[i] == 0 || n >= NR) continue;
+#pragma unroll 1
+            for (int j = 0; j < nb; j++) Jr[n * MB + j] = (j == i) ? (R)1 : (R)0;
+            bb[n] = -dq[i];
+            hi[n] = M.coulomb[i] * dt; lo[n] = -hi[n];
             fidx[n] = -1;
             n++;
         }

@@ -33,6 +33,8 @@ struct PModel {
     R mass[PM_MAXB], cx[PM_MAXB], cy[PM_MAXB], izz[PM_MAXB];
     R ox[PM_MAXB], oy[PM_MAXB];// DART body origin in the planar body frame (add_ext_force point)
     R damping[PM_MAXB], kspring[PM_MAXB], rest[PM_MAXB];
+    R coulomb[PM_MAXB];        // joint Coulomb friction (force); row bounds are +-coulomb*dt
+    int32_t any_coulomb;
     R qlo[PM_MAXB], qhi[PM_MAXB];
     int32_t limited[PM_MAXB];
     R qinit[PM_MAXB], dqinit[PM_MAXB];

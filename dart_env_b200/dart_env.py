@@ -37,7 +37,8 @@ class DartEnv:
                  action_type="continuous", visualize=True, disableViewer=False, screen_width=80, screen_height=45, *,
                  task: Optional[Task] = None, num_envs: int = 1, batched: Optional[bool] = None, output: str = "torch",
                  device: int = 0, seed: Optional[int] = None, world_offset: int = 0, auto_reset: Optional[bool] = None,
-                 max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False):
+                 max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False,
+                 collidable: bool = True):
         assert obs_type in ("parameter", "image")
         assert action_type in ("continuous", "discrete")
         if obs_type == "image":
@@ -54,6 +55,8 @@ class DartEnv:
         if friction_all is not None:
             for b in self.model.bodies:
                 b.friction_coeff = float(friction_all)
+        if not collidable:  # reacher2d.py:11-14: every bodynode set_collidable(False)
+            self.model.shapes, self.model.ground = [], []
         # task=None: physics-only handle; the subclass computes obs / reward / done on the host side
         # (torch ops over the batched state), calling do_simulation() like the reference classes do
         self.fused = task is not None
@@ -76,6 +79,11 @@ class DartEnv:
         self.world_offset = int(world_offset)
         self.disableViewer = True
         self.viewer = None
+        # random perturbation (dart_env.py:74-78): off by default, as in the reference
+        self.add_perturbation = False
+        self.perturbation_parameters = [0.05, 5, 2]  # probability, magnitude, bodyid
+        self.perturbation_duration = 40
+        self.perturb_force = None
         self._device_index = device
         self._f64 = f64
 
@@ -146,6 +154,9 @@ class DartEnv:
         return self.model.dt * self.frame_skip
 
     def reset(self):
+        self.perturbation_duration = 0
+        if self.perturb_force is not None:
+            self._perturb_count.zero_()
         if not self.fused:
             return self._out_obs(self.reset_model())
         obs = self.engine.reset(None, self._obs)
@@ -178,8 +189,29 @@ class DartEnv:
             t = tau.reshape(self.num_envs, -1).to(self.engine.device).contiguous()
         else:
             t = torch.as_tensor(np.asarray(tau, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device).contiguous()
+        fext = None
+        if self.add_perturbation:
+            # dart_env.py:159-172, per world: when the countdown is 0 the force is cleared and, with
+            # probability p, a new +-magnitude force along x or y is drawn; it is applied at the origin of
+            # bodynodes[bodyid] (add_ext_force) on every sub-step of this call.
+            n, dev = self.num_envs, self.engine.device
+            if self.perturb_force is None:
+                self.perturb_force = torch.zeros((n, 3), dtype=t.dtype, device=dev)
+                self._perturb_count = torch.zeros((n,), dtype=torch.int64, device=dev)
+            zero = self._perturb_count == 0
+            self.perturb_force[zero] = 0
+            p, mag, body = self.perturbation_parameters
+            draw = zero & (torch.rand(n, device=dev) < p)
+            axis = torch.randint(0, 2, (n,), device=dev)
+            sign = torch.randint(0, 2, (n,), device=dev) * 2 - 1
+            newf = torch.zeros((n, 3), dtype=t.dtype, device=dev)
+            newf[torch.arange(n, device=dev), axis] = (sign * mag).to(t.dtype)
+            self.perturb_force = torch.where(draw[:, None], newf, self.perturb_force)
+            self._perturb_count = torch.where(zero, self._perturb_count, self._perturb_count - 1)
+            fext = torch.zeros((n, self.model.n_bodies, 3), dtype=t.dtype, device=dev)
+            fext[:, int(body)] = self.perturb_force
         for _ in range(n_frames):
-            self.engine.substep(t)
+            self.engine.substep(t, fext)
 
     def step(self, a):
         if not self.fused:

@@ -167,5 +167,63 @@ class DartDoubleInvertedPendulumEnv(_HostTaskEnv):
         return q, dq
 
 
-CONTACT_FREE = {"DartCartPole-v1": (DartCartPoleEnv, 1000), "DartCartPoleSwingUp-v1": (DartCartPoleSwingUpEnv, 500),
+class DartReacher2dEnv(_HostTaskEnv):
+    """reacher2d.py:5-68 (registered as DartReacher-v1).  Joint Coulomb friction (reacher2d.skel
+    friction 0.05) enters the LCP as +-friction*dt rows (DART JointCoulombFrictionConstraint)."""
+
+    def __init__(self, **kw):
+        self.action_scale = np.array([200.0, 200.0])
+        self.control_bounds = np.array([[1.0, 1.0], [-1.0, -1.0]])
+        DartEnv.__init__(self, "reacher2d.skel", 2, 11, self.control_bounds, dt=0.01, task=None, collidable=False, **kw)
+        dev = self.engine.device
+        self.target = torch.tensor([0.1, 0.01, -0.1], dtype=torch.float64, device=dev).repeat(self.num_envs, 1)
+        self._tip = self.model.n_bodies - 1
+        self._tip_com = tuple(self.model.bodies[self._tip].com)
+
+    def _tip_vec(self, q):
+        return body_point_world(self.model, q, self._tip, self._tip_com) - self.target
+
+    def step(self, a):
+        a = self._action(a)
+        lo = torch.tensor(self.control_bounds[1], device=a.device)
+        hi = torch.tensor(self.control_bounds[0], device=a.device)
+        tau = torch.minimum(torch.maximum(a, lo), hi) * torch.tensor(self.action_scale, device=a.device)
+        self.do_simulation(tau, self.frame_skip)
+        q, dq = self._state()
+        ob = self._obs_from(q, dq)
+        reward = -self._tip_vec(q).norm(dim=1) - (a ** 2).sum(1)
+        return self._finish(ob, reward, torch.zeros(self.num_envs, dtype=torch.bool, device=ob.device))
+
+    def _obs_from(self, q, dq):
+        return torch.cat([torch.cos(q), torch.sin(q), self.target[:, [0, 2]], dq, self._tip_vec(q)], 1)
+
+    def _get_obs(self):
+        return self._obs_from(*self._state())
+
+    def _sample_reset(self, n):
+        q0, dq0 = self._q0()
+        q = q0 + self._uniform(-.01, .01, q0.shape)
+        dq = dq0 + self._uniform(-.005, .005, q0.shape)
+        # rejection-sample the target inside the 0.2 disc of the x-z plane (reacher2d.py:56-60)
+        t = self._uniform(-.2, .2, (n, 3))
+        t[:, 1] = 0.0
+        for _ in range(64):
+            bad = t.norm(dim=1) >= .2
+            if not bool(bad.any()):
+                break
+            t2 = self._uniform(-.2, .2, (n, 3))
+            t2[:, 1] = 0.0
+            t = torch.where(bad[:, None], t2, t)
+        t[:, 1] = 0.01
+        self.target = t
+        return q, dq
+
+    def _reset_worlds(self, mask):
+        old = self.target.clone()
+        super()._reset_worlds(mask)
+        self.target = torch.where(mask[:, None], self.target, old)
+
+
+CONTACT_FREE = {"DartReacher-v1": (DartReacher2dEnv, 50),
+                "DartCartPole-v1": (DartCartPoleEnv, 1000), "DartCartPoleSwingUp-v1": (DartCartPoleSwingUpEnv, 500),
                 "DartDoubleInvertedPendulumEnv-v1": (DartDoubleInvertedPendulumEnv, 1000)}

@@ -151,6 +151,7 @@ class Model:
     shapes: List[Shape]        # robot collision shapes (body-local)
     ground: List[Shape]        # world-fixed collision shapes
     source: str = ""
+    n_static_skeletons: int = 1   # immobile skeletons before the robot (world.skeletons indexing)
 
     @property
     def n_bodies(self) -> int:
@@ -195,6 +196,7 @@ class Model:
 
         return {
             "name": self.name, "dt": self.dt, "gravity": arr(self.gravity), "source": self.source,
+            "n_static_skeletons": self.n_static_skeletons,
             "bodies": [{
                 "name": b.name, "parent": b.parent, "joint_name": b.joint_name,
                 "joint_type": b.joint_type, "dof": b.dof,
@@ -232,7 +234,7 @@ class Model:
         mk = lambda s: Shape(type=s["type"], size=np.array(s["size"]), T=np.array(s["T"]), body=s["body"])
         return Model(name=d["name"], dt=d["dt"], gravity=np.array(d["gravity"]), bodies=bodies,
                      shapes=[mk(s) for s in d["shapes"]], ground=[mk(s) for s in d["ground"]],
-                     source=d.get("source", ""))
+                     source=d.get("source", ""), n_static_skeletons=d.get("n_static_skeletons", 1))
 
     def save_json(self, path: str) -> None:
         with open(path, "w") as fh:
@@ -425,7 +427,7 @@ def parse_skel(path: str, dt: Optional[float] = None) -> Model:
     for j in joints:
         create(j)
     return Model(name=robot_elem.get("name", "robot"), dt=time_step, gravity=gravity, bodies=bodies,
-                 shapes=shapes, ground=ground, source=os.path.basename(path))
+                 shapes=shapes, ground=ground, source=os.path.basename(path), n_static_skeletons=len(skeletons) - 1)
 
 
 # ----------------------------------------------------------------------------- asset lookup

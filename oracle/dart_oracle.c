@@ -49,7 +49,7 @@
 
 #define NB DARTB_MAX_BODIES
 #define MAXC DARTB_MAX_SHAPES /* at most one contact per robot shape / ground shape pair kept */
-#define MAXROWS (3 * MAXC + NB)
+#define MAXROWS (3 * MAXC + 2 * NB)
 
 /* DART constants (ContactConstraint.cpp / JointLimitConstraint.cpp) */
 #define CONTACT_ERP 0.01
@@ -829,6 +829,21 @@ static void solve_constraints(orc_world_t* w) {
         cfm[n] = LIMIT_CFM;
         row_contact[n] = -1;
         w->limit_active[d] = act;
+        n++;
+    }
+    /* JointCoulombFrictionConstraint: one row per dof with Coulomb friction and non-zero velocity,
+     * b = -dq, impulse bounds +-friction*dt ("Coulomb friction is force not impulse"), CFM 1e-9.
+     * DART activates them after the joint-limit constraints (ConstraintSolver::updateConstraints). */
+    for (int d = 0; d < nd; d++) {
+        const dartb_body_t* bd = &w->m.bodies[w->dof_body[d]];
+        if (bd->coulomb == 0.0 || w->dq[d] == 0.0 || n >= MAXROWS) continue;
+        for (int k = 0; k < nd; k++) J[n][k] = 0;
+        J[n][d] = 1.0;
+        b[n] = -w->dq[d];
+        hi[n] = bd->coulomb * w->m.dt; lo[n] = -hi[n];
+        findex[n] = -1;
+        cfm[n] = LIMIT_CFM;
+        row_contact[n] = -1;
         n++;
     }
     w->nrows = n;

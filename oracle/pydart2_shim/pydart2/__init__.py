@@ -106,9 +106,27 @@ class _BodyNode(object):
     def com_spatial_velocity(self):
         return self._ow.body_com_spatial_velocity(self.id)
 
+    def set_collidable(self, flag):
+        if not flag:
+            m = self._skel._model
+            m.shapes = [s for s in m.shapes if s.body != self.id]
+            self._skel._world._rebuild()
+
     def add_ext_force(self, _force, _offset=None, _isForceLocal=False, _isOffsetLocal=True):
         assert _offset is None and not _isForceLocal, "shim supports the call form the reference uses"
         self._ow.add_ext_force(self.id, np.asarray(_force, dtype=np.float64))
+
+
+class _StaticBody(object):
+    """a body of an immobile skeleton: only set_collidable(False) is meaningful"""
+
+    def __init__(self, world):
+        self._world = world
+
+    def set_collidable(self, flag):
+        if not flag:
+            self._world._model.ground = []
+            self._world._rebuild()
 
 
 class _Skeleton(object):
@@ -116,19 +134,27 @@ class _Skeleton(object):
         self._world, self._model, self.is_mobile = world, model, mobile
         self.name = model.name if model is not None else "ground skeleton"
         if model is None:
-            self.bodynodes, self.joints, self.ndofs = [], [], 0
+            self.joints, self.ndofs = [], 0
+            self.bodynodes = [_StaticBody(world)]
             return
         self.bodynodes = [_BodyNode(self, i) for i in range(model.n_bodies)]
         self.name_to_body = {b.name: b for b in self.bodynodes}
         self.joints = [_Joint(self, i) for i in range(model.n_bodies)]
         self.ndofs = model.n_dofs
 
+    def set_self_collision_check(self, flag):
+        pass  # self-collision is never on for the in-scope skeletons
+
     @property
     def q(self):
+        if self._model is None:
+            return SkelVector(np.zeros(6))
         return SkelVector(self._world._ow.get_state()[0])
 
     @q.setter
     def q(self, v):
+        if self._model is None:
+            return  # moving an immobile, non-collidable marker (reacher2d target) has no dynamic effect
         self.set_positions(v)
 
     @property
@@ -168,7 +194,8 @@ class World(object):
             raise NotImplementedError("shim only loads .skel worlds")
         self._model = parse_skel(skel_path, step)
         self._ow = OracleWorld(self._model)
-        self.skeletons = [_Skeleton(self, None, mobile=False), _Skeleton(self, self._model)]
+        self.skeletons = [_Skeleton(self, None, mobile=False) for _ in range(self._model.n_static_skeletons)]
+        self.skeletons.append(_Skeleton(self, self._model))
         self.collision_result = _CollisionResult(self)
         self.frame = 0
 

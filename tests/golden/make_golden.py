@@ -40,6 +40,7 @@ REF_CLASSES_CF = {
     "DartCartPoleSwingUp-v1": ("gym.envs.dart.cartpole_swingup", "DartCartPoleSwingUpEnv", "cartpole_swingup.skel", 0.01),
     "DartDoubleInvertedPendulumEnv-v1": ("gym.envs.dart.inverted_double_pendulum", "DartDoubleInvertedPendulumEnv",
                                          "inverted_double_pendulum.skel", 0.01),
+    "DartReacher-v1": ("gym.envs.dart.reacher2d", "DartReacher2dEnv", "reacher2d.skel", 0.01),
 }
 MAXC = 8
 
@@ -50,11 +51,13 @@ def contact_free_rollouts(env_id, n_steps, seed):
     env = getattr(importlib.import_module(mod), cls)()
     env.seed(seed)
     rng = np.random.RandomState(seed)
-    rec = {k: [] for k in ("q", "dq", "action", "obs", "reward", "done", "q2", "dq2")}
+    rec = {k: [] for k in ("q", "dq", "action", "obs", "reward", "done", "q2", "dq2", "target")}
+    nact = env.action_space.shape[0]
     for scale in (1.0, 0.3, 0.05):
         env.reset()
         for t in range(n_steps):
-            a = rng.uniform(-1, 1, 1) * scale
+            a = rng.uniform(-1.2, 1.2, nact) * scale
+            rec["target"].append(np.array(getattr(env, "target", np.zeros(3)), dtype=np.float64))
             s0 = env.state_vector()
             ob, r, d, _ = env.step(a)
             s1 = env.state_vector()
@@ -222,7 +225,7 @@ def main_contact_free():
     for env_id in REF_CLASSES_CF:
         roll = contact_free_rollouts(env_id, n_steps=80, seed=5)
         name = {"DartCartPole-v1": "cartpole", "DartCartPoleSwingUp-v1": "cartpole_swingup",
-                "DartDoubleInvertedPendulumEnv-v1": "double_pendulum"}[env_id]
+                "DartDoubleInvertedPendulumEnv-v1": "double_pendulum", "DartReacher-v1": "reacher2d"}[env_id]
         path = os.path.join(outdir, name + ".npz")
         np.savez_compressed(path, env_id=env_id, **roll)
         print(env_id, "->", path, "steps", len(roll["step_q"]), "done", int(roll["step_done"].sum()), os.path.getsize(path) // 1024, "KiB")

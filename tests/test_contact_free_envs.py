@@ -16,13 +16,26 @@ from tools.host_emu import emu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {"DartCartPole-v1": ("cartpole.npz", "cartpole.skel", 0.02, 100.0),
          "DartCartPoleSwingUp-v1": ("cartpole_swingup.npz", "cartpole_swingup.skel", 0.01, 40.0),
-         "DartDoubleInvertedPendulumEnv-v1": ("double_pendulum.npz", "inverted_double_pendulum.skel", 0.01, 40.0)}
+         "DartDoubleInvertedPendulumEnv-v1": ("double_pendulum.npz", "inverted_double_pendulum.skel", 0.01, 40.0),
+         "DartReacher-v1": ("reacher2d.npz", "reacher2d.skel", 0.01, 200.0)}
 
 
 def _model(skel, dt):
     m = load_model(skel, dt)
     m.enforce_limits()
+    if skel == "reacher2d.skel":  # reacher2d.py:11-14 set_collidable(False) on every body
+        m.shapes, m.ground = [], []
     return m
+
+
+def _tau(env_id, g, scale):
+    a = g["step_action"]
+    tau = np.zeros_like(g["step_q"])
+    if env_id == "DartReacher-v1":
+        tau[:] = np.clip(a, -1, 1) * scale
+    else:
+        tau[:, 0] = a[:, 0] * scale
+    return tau
 
 
 @pytest.mark.parametrize("env_id", list(CASES))
@@ -33,8 +46,7 @@ def test_loop_kernel_source_steps_contact_free_models(env_id):
     m = _model(skel, dt)
     assert "loop:generic" in capi.describe(m, Task.physics_only(2))
     q, dq = g["step_q"].copy(), g["step_dq"].copy()
-    tau = np.zeros_like(q)
-    tau[:, 0] = g["step_action"][:, 0] * scale
+    tau = _tau(env_id, g, scale)
     for _ in range(2):  # frame_skip
         q, dq, *_ = emu.substep(m, Task.physics_only(2), q, dq, tau, f64=True, variant=1)
     assert np.allclose(q, g["step_q2"], rtol=1e-9, atol=1e-10)
@@ -57,6 +69,8 @@ def test_batched_env_matches_reference_classes(env_id):
     env = make(env_id, num_envs=n, output="numpy", seed=0, auto_reset=False, f64=True)
     assert "loop:generic" in env.engine.kernel_name
     env.set_state(g["step_q"], g["step_dq"])
+    if env_id == "DartReacher-v1":
+        env.target = torch.tensor(g["step_target"], device="cuda")
     ob, rew, done, _ = env.step(g["step_action"])
     s = env.state_vector()
     nd = g["step_q"].shape[1]
@@ -76,6 +90,6 @@ def test_batched_env_matches_reference_classes(env_id):
     env = make(env_id, num_envs=64, output="torch", seed=2)
     env.reset()
     for _ in range(60):
-        o, r, d, _ = env.step(torch.rand((64, 1), device="cuda") * 2 - 1)
+        o, r, d, _ = env.step(torch.rand((64, env.act_dim), device="cuda") * 2 - 1)
     assert torch.isfinite(o).all()
     env.close()

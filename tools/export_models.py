@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from dart_env_b200.skel import find_asset, parse_skel  # noqa: E402
 from dart_env_b200.tasks import SPECS  # noqa: E402
 
-EXTRA = ["cartpole.skel", "cartpole_swingup.skel", "inverted_double_pendulum.skel"]
+EXTRA = ["cartpole.skel", "cartpole_swingup.skel", "inverted_double_pendulum.skel", "reacher2d.skel"]
 for skel in [spec.skel for spec in SPECS.values()] + EXTRA:
     class spec:  # noqa: N801
         pass

@@ -24,7 +24,7 @@ def lib():
     return _LIB
 
 
-def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_iters=30, maxc=8, variant=0):
+def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_iters=30, maxc=8, variant=0, hints=None):
     L = lib()
     cm, ct = pack_model(model), pack_task(task)
     q = np.ascontiguousarray(q, dtype=np.float64)
@@ -39,7 +39,8 @@ def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_
     data = np.zeros((n, maxc, 10), dtype=np.float32)
     rc = L.emu_substep(C.byref(cm), C.byref(ct), int(f64), n, dp(q), dp(dq), dp(tau), dp(fext), lcp_mode, pgs_iters,
                        dp(q2), dp(dq2), cnt.ctypes.data_as(C.POINTER(C.c_int32)), body.ctypes.data_as(C.POINTER(C.c_int32)),
-                       data.ctypes.data_as(C.POINTER(C.c_float)), maxc, int(variant))
+                       data.ctypes.data_as(C.POINTER(C.c_float)), maxc, int(variant),
+                       None if hints is None else hints.ctypes.data_as(C.POINTER(C.c_uint64)))
     if rc:
         raise RuntimeError(L.emu_last_error().decode())
     return q2, dq2, cnt, body, data

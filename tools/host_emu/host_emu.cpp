@@ -12,7 +12,7 @@
 template <class T, typename R>
 static void run_substep(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
                         const double* fext, int lcp_mode, int pgs_iters, double* q_out, double* dq_out, int32_t* count,
-                        int32_t* body, float* data, int maxc) {
+                        int32_t* body, float* data, int maxc, uint64_t* hints) {
     constexpr int NB = T::NB;
     for (int w = 0; w < n; w++) {
         R q[NB], dq[NB], tau[NB], eft[NB], efx[NB], efy[NB];
@@ -30,9 +30,9 @@ static void run_substep(const PModel<R>& M, int n, const double* q_in, const dou
                 const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
                 eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
             }
-            substep<T, R, true, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+            { uint64_t hint = ~(uint64_t)0; substep<T, R, true, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, hint); }
         } else {
-            substep<T, R, false, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+            { uint64_t hint = hints ? hints[w] : ~(uint64_t)0; substep<T, R, false, false>(M, q, dq, tau, eft, efx, efy, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, hint); if (hints) hints[w] = hint; }
         }
         for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)q[i]; dq_out[w * NB + i] = (double)dq[i]; }
     }
@@ -77,7 +77,8 @@ extern "C" const char* emu_last_error() { return g_err.c_str(); }
 // returns 0 ok; arrays are [n, nd] row-major doubles (converted to the kernel precision inside)
 extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task, int f64, int n, const double* q,
                            const double* dq, const double* tau, const double* fext, int lcp_mode, int pgs_iters,
-                           double* q_out, double* dq_out, int32_t* count, int32_t* body, float* data, int maxc, int variant) {
+                           double* q_out, double* dq_out, int32_t* count, int32_t* body, float* data, int maxc, int variant,
+                           uint64_t* hints) {
     lower::Result res;
     std::string why = lower::lower_model(*model, *task, res);
     if (!why.empty()) { g_err = why; return 1; }
@@ -90,8 +91,8 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
     }
 #define RUN(T)                                                                                                          \
     if (res.signature == T::sig) {                                                                                       \
-        if (f64) run_substep<T, double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
-        else run_substep<T, float>(mf, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);          \
+        if (f64) run_substep<T, double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, hints); \
+        else run_substep<T, float>(mf, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, hints);          \
         return 0;                                                                                                        \
     }
     RUN(TopoHopper) RUN(TopoWalker) RUN(TopoCheetah) RUN(TopoSnake)
