@@ -393,7 +393,20 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     int rc = e->f64 ? launch_step<double>(e, e->d_stage, d_obs, d_rew, d_done, auto_reset, st)
                     : launch_step<float>(e, e->d_stage, d_obs, d_rew, d_done, auto_reset, st);
     if (rc) return rc;
-    // one D2H for obs | reward | done
+    // results: DMA straight into the caller's buffers when they are page-locked (the DartEnv wrapper
+    // allocates its output arrays pinned), else one D2H into the pinned staging block + memcpy
+    cudaPointerAttributes pa;
+    const bool direct = cudaPointerGetAttributes(&pa, h_obs) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&pa, h_reward) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&pa, h_done) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // a pageable pointer may leave cudaErrorInvalidValue behind on old drivers
+    if (direct) {
+        CK(cudaMemcpyAsync(h_obs, d_obs, fo * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_reward, d_rew, fr * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
     CK(cudaMemcpyAsync(e->h_stage + fa, d_obs, (fo + fr + fd) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     std::memcpy(h_obs, e->h_stage + fa, fo * 4);

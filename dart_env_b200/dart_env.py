@@ -38,7 +38,7 @@ class DartEnv:
                  task: Optional[Task] = None, num_envs: int = 1, batched: Optional[bool] = None, output: str = "torch",
                  device: int = 0, seed: Optional[int] = None, world_offset: int = 0, auto_reset: Optional[bool] = None,
                  max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False,
-                 collidable: bool = True):
+                 collidable: bool = True, copy: bool = True):
         assert obs_type in ("parameter", "image")
         assert action_type in ("continuous", "discrete")
         if obs_type == "image":
@@ -77,6 +77,7 @@ class DartEnv:
         self.output = output if self.batched else "numpy"
         self.auto_reset = self.batched if auto_reset is None else bool(auto_reset)
         self.world_offset = int(world_offset)
+        self.copy = bool(copy)  # sync_vector_env.py:44-47: return a copy of the observation buffer
         self.disableViewer = True
         self.viewer = None
         # random perturbation (dart_env.py:74-78): off by default, as in the reference
@@ -119,9 +120,10 @@ class DartEnv:
         self._h_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory()
         self._h_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
         self._h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
-        self._n_obs = np.empty((n, self.obs_dim), dtype=np.float32)
-        self._n_rew = np.empty((n,), dtype=np.float32)
-        self._n_done = np.empty((n,), dtype=np.uint8)
+        # page-locked output arrays of the host path: dartb_step_host DMAs straight into them
+        self._n_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory().numpy()
+        self._n_rew = torch.empty((n,), dtype=torch.float32).pin_memory().numpy()
+        self._n_done = torch.empty((n,), dtype=torch.uint8).pin_memory().numpy()
 
     @property
     def max_episode_steps(self):
@@ -227,7 +229,8 @@ class DartEnv:
                 infos = {}
                 if self._max_episode_steps:
                     infos["TimeLimit.truncated"] = self.engine.truncated().cpu().numpy().astype(bool)
-                return self._n_obs.copy(), self._n_rew.astype(np.float64), self._n_done.astype(np.bool_), infos
+                obs = self._n_obs.copy() if self.copy else self._n_obs  # gym VectorEnv(copy=...) semantics
+                return obs, self._n_rew.astype(np.float64), self._n_done.astype(np.bool_), infos
             info = {}
             done = bool(self._n_done[0])
             if self._max_episode_steps and done:
