@@ -223,7 +223,7 @@ def run_ours(args, rank, local_rank, world_size):
     torch.cuda.synchronize()
     warm_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    done_frac = float(done.float().mean().item())
+    done_frac = float((done != 0).float().mean().item())
 
     # ---- end to end through the public host API (numpy in / numpy out, pinned staging)
     henv = make(args.env, num_envs=n, output="numpy", device=local_rank, seed=args.seed, world_offset=rank * n, batched=True)

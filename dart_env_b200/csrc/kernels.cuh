@@ -193,7 +193,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
             a.dq[(size_t)i * a.n + w] = dq[i];
         });
         a.reward[w] = (float)r;
-        a.done[w] = done ? 1 : 0;
+        a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
         if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
     }
 }
@@ -392,7 +392,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     if (active) {
         for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
         a.reward[w] = (float)r;
-        a.done[w] = done ? 1 : 0;
+        a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
         if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
     }
 }

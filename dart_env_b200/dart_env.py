@@ -225,16 +225,17 @@ class DartEnv:
             # host path: one library call does pinned H2D, the launch, one D2H and the sync
             act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
             self.engine.step_host(act, self._n_obs, self._n_rew, self._n_done, self.auto_reset)
+            d = self._n_done  # bit 0 done, bit 1 truncated by the time limit (no extra transfer)
             if self.batched:
                 infos = {}
                 if self._max_episode_steps:
-                    infos["TimeLimit.truncated"] = self.engine.truncated().cpu().numpy().astype(bool)
+                    infos["TimeLimit.truncated"] = (d & 2) != 0
                 obs = self._n_obs.copy() if self.copy else self._n_obs  # gym VectorEnv(copy=...) semantics
-                return obs, self._n_rew.astype(np.float64), self._n_done.astype(np.bool_), infos
+                return obs, self._n_rew.astype(np.float64), d != 0, infos
             info = {}
-            done = bool(self._n_done[0])
+            done = bool(d[0] != 0)
             if self._max_episode_steps and done:
-                info["TimeLimit.truncated"] = bool(self.engine.truncated()[0].item())
+                info["TimeLimit.truncated"] = bool(d[0] & 2)
             return self._n_obs[0].astype(np.float64), float(self._n_rew[0]), done, info
         if self.batched and self.output == "torch":
             return self._obs, self._rew, self._done.bool(), {}

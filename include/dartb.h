@@ -133,7 +133,9 @@ int dartb_get_state_f64(dartb_handle_t h, double* d_q, double* d_dq, void* strea
 /* One env.step(): clamp/scale action, frame_skip x {set_forces; world.step()}, obs/reward/done,
  * optional auto-reset of done worlds (gym/vector/sync_vector_env.py:76-79 semantics: the returned
  * obs of a done world is its reset obs).  d_action [n,n_act], d_obs [n,n_obs], d_reward [n],
- * d_done uint8[n].  (hopper.py:24-65 and siblings; dart_env.py:158-175) */
+ * d_done uint8[n]: non-zero = done; bit 1 set = the episode was cut by the time limit only
+ * (info['TimeLimit.truncated'], gym/wrappers/time_limit.py:18-20).
+ * (hopper.py:24-65 and siblings; dart_env.py:158-175) */
 int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_reward,
                uint8_t* d_done, int32_t auto_reset, void* stream);
 
