@@ -65,9 +65,10 @@ struct dartb_engine {
     int lcp_mode = 0, pgs_iters = 30, max_episode_steps = 0;
     int variant_request = -1;                 // -1 auto (DARTB_VARIANT env or static if available), 0, 1
     int variant = 0;                          // 0 = unrolled static topology, 1 = loop / generic topology
+    int wpw_request = 0;                      // worlds per warp of k_env_step, 0 = auto (wpw_for)
     int64_t launches = 0;
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
-    float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_floats = 0;
+    float* h_stage = nullptr; float* d_stage = nullptr; float* h_stage_dev = nullptr; size_t stage_floats = 0;
     std::string kernel_name;
 };
 
@@ -132,6 +133,22 @@ static int block_for(int n) {
     return n <= 148 * 32 * 4 ? 32 : (n <= 148 * 64 * 8 ? 64 : 128);
 }
 
+// Worlds per warp of k_env_step.  The stepper is latency-bound per warp (ncu: IPC ~0.1 with one warp per SM)
+// and a warp executes the UNION of its worlds' branches (contact sets, LCP size classes), so while the
+// grid does not yet fill the 148 x 4 warp schedulers a batch is spread over MORE, narrower warps: fewer
+// worlds per warp = a shorter union path, and the idle schedulers run them concurrently.
+// DARTB_WPW / DARTB_OPT_WORLDS_PER_WARP override.
+static int wpw_for(const dartb_engine* e) {
+    static int forced = -1;
+    if (forced < 0) { const char* ev = getenv("DARTB_WPW"); forced = ev ? atoi(ev) : 0; }
+    int w = e->wpw_request > 0 ? e->wpw_request : forced;
+    if (w >= 1 && w <= 32) return w;
+    const int slots = 148 * 4 * 2;   // two warps per scheduler still interleave without queueing
+    w = 32;
+    while (w > 8 && (e->n + w / 2 - 1) / (w / 2) <= slots) w /= 2;
+    return w;
+}
+
 template <typename R>
 static StepArgs<R> make_args(dartb_engine* e) {
     StepArgs<R> a;
@@ -174,7 +191,9 @@ static int launch_step(dartb_engine* e, const float* action, float* obs, float* 
                        cudaStream_t st) {
     StepArgs<R> a = make_args<R>(e);
     a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.auto_reset = auto_reset;
-    const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
+    a.wpw = wpw_for(e);
+    const int warps = (e->n + a.wpw - 1) / a.wpw;
+    const int bs = block_for(warps * 32), grid = (warps + bs / 32 - 1) / (bs / 32);
     const PTask<R>& K = Sel<R>::t(e);
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     const size_t shm = (size_t)(bs / 32) * 32 * stage * sizeof(float);
@@ -321,6 +340,9 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             if (value != 0 && value != 1) return fail("kernel variant must be 0 (unrolled) or 1 (loop)");
             e->variant_request = (int)value;
             return lower_into(e);
+        case DARTB_OPT_WORLDS_PER_WARP:
+            if (value < 0 || value > 32) return fail("worlds per warp must be 0 (auto) or 1..32");
+            e->wpw_request = (int)value; return 0;
         case DARTB_OPT_MAX_EPISODE_STEPS:
             if (value < 0) return fail("bad max_episode_steps");
             e->max_episode_steps = (int)value; return 0;
@@ -367,6 +389,18 @@ int dartb_step(dartb_handle_t e, const float* d_action, float* d_obs, float* d_r
                   : launch_step<float>(e, d_action, d_obs, d_reward, d_done, auto_reset, (cudaStream_t)stream);
 }
 
+// device-visible alias of a page-locked host pointer (UVA: normally the same value), or null if the
+// memory is pageable
+static void* mapped_alias(const void* h) {
+    cudaPointerAttributes pa;
+    void* d = nullptr;
+    if (cudaPointerGetAttributes(&pa, h) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+        cudaHostGetDevicePointer(&d, const_cast<void*>(h), 0) == cudaSuccess)
+        return d;
+    cudaGetLastError();  // a pageable pointer may leave cudaErrorInvalidValue behind on old drivers
+    return nullptr;
+}
+
 int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done,
                     int32_t auto_reset, void* stream) {
     if (!e) return fail("null handle");
@@ -380,11 +414,40 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     if (e->stage_floats < need) {
         if (e->h_stage) cudaFreeHost(e->h_stage);
         if (e->d_stage) cudaFree(e->d_stage);
-        CK(cudaMallocHost((void**)&e->h_stage, need * 4));
+        e->h_stage = nullptr; e->d_stage = nullptr; e->h_stage_dev = nullptr; e->stage_floats = 0;
+        CK(cudaHostAlloc((void**)&e->h_stage, need * 4, cudaHostAllocMapped));
         CK(cudaMalloc((void**)&e->d_stage, need * 4));
+        void* alias = nullptr;
+        if (cudaHostGetDevicePointer(&alias, e->h_stage, 0) == cudaSuccess) e->h_stage_dev = (float*)alias;
+        cudaGetLastError();
         e->stage_floats = need;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    static int zc_env = -1;
+    if (zc_env < 0) { const char* ev = getenv("DARTB_ZEROCOPY"); zc_env = ev ? atoi(ev) : 1; }
+    if (zc_env && e->h_stage_dev) {
+        // Zero-copy: the step kernel reads the actions from, and writes obs / reward / done to, page-locked
+        // host memory over PCIe itself (coalesced 128 B lines through its shared-memory staging), so the
+        // whole host step is ONE launch + ONE sync: no memcpy nodes (each costs ~5 us of latency, more than
+        // moving these ~250 KB does).  Pageable caller buffers go through the pinned staging block.
+        const float* a_dev = (const float*)mapped_alias(h_action);
+        if (!a_dev) { std::memcpy(e->h_stage, h_action, fa * 4); a_dev = e->h_stage_dev; }
+        float* o_dev = (float*)mapped_alias(h_obs);
+        float* r_dev = (float*)mapped_alias(h_reward);
+        uint8_t* d_dev = (uint8_t*)mapped_alias(h_done);
+        const bool direct = o_dev && r_dev && d_dev;
+        if (!direct) { o_dev = e->h_stage_dev + fa; r_dev = o_dev + fo; d_dev = (uint8_t*)(r_dev + fr); }
+        int rc = e->f64 ? launch_step<double>(e, a_dev, o_dev, r_dev, d_dev, auto_reset, st)
+                        : launch_step<float>(e, a_dev, o_dev, r_dev, d_dev, auto_reset, st);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(st));
+        if (!direct) {
+            std::memcpy(h_obs, e->h_stage + fa, fo * 4);
+            std::memcpy(h_reward, e->h_stage + fa + fo, fr * 4);
+            std::memcpy(h_done, e->h_stage + fa + fo + fr, (size_t)n);
+        }
+        return 0;
+    }
     std::memcpy(e->h_stage, h_action, fa * 4);
     CK(cudaMemcpyAsync(e->d_stage, e->h_stage, fa * 4, cudaMemcpyHostToDevice, st));
     float* d_obs = e->d_stage + fa;
@@ -395,11 +458,7 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     if (rc) return rc;
     // results: DMA straight into the caller's buffers when they are page-locked (the DartEnv wrapper
     // allocates its output arrays pinned), else one D2H into the pinned staging block + memcpy
-    cudaPointerAttributes pa;
-    const bool direct = cudaPointerGetAttributes(&pa, h_obs) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                        cudaPointerGetAttributes(&pa, h_reward) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                        cudaPointerGetAttributes(&pa, h_done) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-    cudaGetLastError();  // a pageable pointer may leave cudaErrorInvalidValue behind on old drivers
+    const bool direct = mapped_alias(h_obs) && mapped_alias(h_reward) && mapped_alias(h_done);
     if (direct) {
         CK(cudaMemcpyAsync(h_obs, d_obs, fo * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_reward, d_rew, fr * 4, cudaMemcpyDeviceToHost, st));

@@ -25,6 +25,7 @@ struct StepArgs {
     uint8_t* done;       // [n]
     const uint8_t* mask; // reset mask (k_reset) or null
     int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
+    int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for
     uint64_t seed;
     int64_t world_offset;
     ContactSink<R> sink;
@@ -95,10 +96,10 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int wb = w - lane;                          // first world of this warp
-    const int cnt = min(32, a.n - wb);                // worlds this warp owns (<= 0: idle warp)
-    const bool active = w < a.n;
+    const int wb = (blockIdx.x * (blockDim.x >> 5) + warp) * a.wpw;   // first world of this warp
+    const int w = wb + lane;
+    const int cnt = min(a.wpw, a.n - wb);             // worlds this warp owns (<= 0: idle warp)
+    const bool active = lane < cnt;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     float* sw = smem + warp * 32 * stage;
 
@@ -322,9 +323,9 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     extern __shared__ float smem[];
     const int nb = M.nb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int wb = w - lane, cnt = min(32, a.n - wb);
-    const bool active = w < a.n;
+    const int wb = (blockIdx.x * (blockDim.x >> 5) + warp) * a.wpw;
+    const int w = wb + lane, cnt = min(a.wpw, a.n - wb);
+    const bool active = lane < cnt;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     float* sw = smem + warp * 32 * stage;
     if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];

@@ -37,9 +37,12 @@
 #endif
 #ifdef DARTB_HOST_EMU
 extern long g_emu_counters[8];  // [0] exact LCP calls [1] solved by lcp_small<4> [2] by lcp_small<8> [3] Dantzig [4] BPP iterations
+extern long g_emu_hist[32];     // LCP row-count histogram (all lcp_exact calls)
 #define EMU_COUNT(i, v) (g_emu_counters[i] += (v))
+#define EMU_HIST(n) (g_emu_hist[(n) < 31 ? (n) : 31]++)
 #else
 #define EMU_COUNT(i, v) ((void)0)
+#define EMU_HIST(n) ((void)0)
 #endif
 
 // max of v over the lanes of this warp that are currently executing this code
@@ -622,6 +625,7 @@ DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int
     const int nmax = warp_max_active(n);
     bool ok = false;
     EMU_COUNT(0, 1);
+    EMU_HIST(n);
     if (nmax <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (nmax <= 6 && NR > 4) { ok = lcp_small<R, 6>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (NR > 6) {

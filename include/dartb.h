@@ -105,7 +105,8 @@ enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
        DARTB_OPT_PGS_ITERS = 2,
        DARTB_OPT_FRICTION_ALL = 3,/* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */
        DARTB_OPT_MAX_EPISODE_STEPS = 4,/* TimeLimit (gym/wrappers/time_limit.py:14-21); 0 = off */
-       DARTB_OPT_KERNEL_VARIANT = 5 /* 0 = unrolled per-topology kernel, 1 = loop / topology-generic kernel */ };
+       DARTB_OPT_KERNEL_VARIANT = 5, /* 0 = unrolled per-topology kernel, 1 = loop / topology-generic kernel */
+       DARTB_OPT_WORLDS_PER_WARP = 6 /* launch shape of dartb_step: worlds per warp, 0 = auto; results do not depend on it */ };
 
 typedef struct dartb_engine* dartb_handle_t;
 
@@ -139,10 +140,12 @@ int dartb_get_state_f64(dartb_handle_t h, double* d_q, double* d_dq, void* strea
 int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_reward,
                uint8_t* d_done, int32_t auto_reset, void* stream);
 
-/* The same env.step() for HOST buffers (numpy arrays of the reference-facing wrapper): copies the
- * actions through pinned staging to the device, launches, copies obs | reward | done back with one
- * transfer and synchronises.  h_* are ordinary host pointers.  This is the end-to-end call a
- * DartEnv user makes per step (bench.py "e2e"). */
+/* The same env.step() for HOST buffers (numpy arrays of the reference-facing wrapper), synchronous:
+ * when it returns, h_obs / h_reward / h_done hold the results.  h_* are ordinary host pointers.
+ * Page-locked buffers are read / written by the step kernel itself over PCIe (zero-copy: one launch
+ * and one sync, no memcpy nodes); pageable ones go through the library's pinned staging block.
+ * DARTB_ZEROCOPY=0 selects the explicit H2D / D2H copy path instead.  This is the end-to-end call
+ * a DartEnv user makes per step (bench.py "e2e"). */
 int dartb_step_host(dartb_handle_t h, const float* h_action, float* h_obs, float* h_reward,
                     uint8_t* h_done, int32_t auto_reset, void* stream);
 

@@ -27,7 +27,7 @@ e0.record()
 for i in range(K): eng.step(acts[i %% 16], env._obs, env._rew, env._done, True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print("%%-20s n=%%7d block=%%4s lcp=%%s %%8.1f us/step  %%.3e env-steps/s  [%%s]" %% (env_id, n, os.environ.get("DARTB_BLOCK", "auto"), os.environ.get("SWEEP_PGS", "exact"), ms * 1e3, n / (ms * 1e-3), eng.kernel_name))
+print("%%-20s n=%%7d wpw=%%4s block=%%4s lcp=%%s %%8.1f us/step  %%.3e env-steps/s  [%%s]" %% (env_id, n, os.environ.get("DARTB_WPW", "auto"), os.environ.get("DARTB_BLOCK", "auto"), os.environ.get("SWEEP_PGS", "exact"), ms * 1e3, n / (ms * 1e-3), eng.kernel_name))
 ''' % ROOT
 
 cfgs = []
@@ -44,6 +44,14 @@ elif mode == "lcp":
             for n in (4096, 65536):
                 cfgs.append(("DartHopper-v1", n, "32" if n == 4096 else "128", v, pgs))
             cfgs.append(("DartHalfCheetah-v1", 16384, "128", v, pgs))
+elif mode == "wpw":
+    for env_id, n in (("DartHopper-v1", 4096), ("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384),
+                      ("DartSnake7Link-v1", 4096), ("DartHopper-v1", 16384), ("DartHopper-v1", 65536)):
+        for wpw in ("32", "16", "8", "4", "2"):
+            if n // int(wpw) > 16384:
+                continue
+            for b in ("32", "128"):
+                cfgs.append((env_id, n, b, "0", "", wpw))
 else:
     for b in ("32", "64", "128", "256"):
         cfgs.append(("DartHopper-v1", 4096, b, "0"))
@@ -52,5 +60,7 @@ for cfg in cfgs:
     env = dict(os.environ, DARTB_BLOCK=b, DARTB_VARIANT=v, DART_ENV_NO_REFERENCE="1")
     if len(cfg) > 4 and cfg[4]:
         env["SWEEP_PGS"] = cfg[4]
+    if len(cfg) > 5:
+        env["DARTB_WPW"] = cfg[5]
     r = subprocess.run([sys.executable, "-c", CODE, env_id, str(n)], env=env, capture_output=True, text=True)
     print("variant=%s " % v + (r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)

@@ -68,6 +68,8 @@ static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, cons
 }
 
 long g_emu_counters[8];
+long g_emu_hist[32];
+extern "C" void emu_hist(long* out, int reset) { for (int i = 0; i < 32; i++) { out[i] = g_emu_hist[i]; if (reset) g_emu_hist[i] = 0; } }
 extern "C" void emu_counters(long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = g_emu_counters[i]; if (reset) g_emu_counters[i] = 0; } }
 
 static std::string g_err;
