@@ -12,14 +12,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-SO = os.path.join(HERE, "libdartb.so")
+# developer A/B builds: DARTB_SO_SUFFIX=_x DARTB_NVCC_FLAGS="-DFOO" give libdartb_x.so next to the product library
+_SFX = os.environ.get("DARTB_SO_SUFFIX", "")
+OBJ = os.path.join(HERE, "build" + _SFX)
+SO = os.path.join(HERE, "libdartb%s.so" % _SFX)
 DEPS = ["dartb.cu", "inst.cu", "kernels.cuh", "planar_kernels.cuh", "planar_loop.cuh", "planar_model.h", "lower.h",
         os.path.join("..", "..", "include", "dartb.h")]
 INSTANCES = [("hopper", "TopoHopper"), ("walker", "TopoWalker"), ("cheetah", "TopoCheetah"), ("snake", "TopoSnake"),
              ("loop", None)]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("DARTB_NVCC_FLAGS", "").split()
 
 
 def nvcc_path() -> str:

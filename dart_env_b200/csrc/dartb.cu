@@ -143,7 +143,9 @@ static int wpw_for(const dartb_engine* e) {
     if (forced < 0) { const char* ev = getenv("DARTB_WPW"); forced = ev ? atoi(ev) : 0; }
     int w = e->wpw_request > 0 ? e->wpw_request : forced;
     if (w >= 1 && w <= 32) return w;
-    const int slots = 148 * 4 * 2;   // two warps per scheduler still interleave without queueing
+    // one warp per scheduler: measured (gpurun_out/sweep_wpw.log) a second narrower warp per scheduler
+    // costs more than the shorter union path saves (Walker2d 16384 worlds: 224 us at 16/warp vs 173 at 32)
+    const int slots = 148 * 4;
     w = 32;
     while (w > 8 && (e->n + w / 2 - 1) / (w / 2) <= slots) w /= 2;
     return w;

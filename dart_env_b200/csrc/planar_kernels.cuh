@@ -516,6 +516,187 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     return true;
 }
 
+// ------------------------------------------------------------------------ K6 fast path, tableau form
+// The same block-principal-pivoting iteration as lcp_small (same sets visited, same rounding-aware
+// tests), with the linear algebra kept as a PRINCIPAL PIVOT TRANSFORM of A instead of a fresh masked
+// Cholesky per iteration: with F the free rows and B the bound ones, the tableau T maps
+// z = [b_F ; x_B] to y = [x_F ; (w + b)_B].  Moving one row between F and B is one symmetric
+// exchange step on T ((NM-1)^2 FMAs, pivot T_kk > 0 for the positive-definite A), so an iteration
+// costs (rows that changed set) exchanges + one NM x NM product, and stage 2 (friction bounds fixed
+// from the frictionless normals, ODE dSolveLCP semantics) CONTINUES from stage 1's tableau.
+// ncu (profiles/r1_hopper_v3_stages.md): the Cholesky form was 28 % of the kernel's instructions.
+template <int K, typename R, int NM>
+DEVI bool ppt_exchange(R (&T)[NM][NM]) {
+    const R d = T[K][K];
+    if (!(d > 0)) return false;
+    const R p = Num<R>::rcp_(d);
+    R rk[NM];
+#pragma unroll
+    for (int j = 0; j < NM; j++) rk[j] = T[K][j] * p;
+#pragma unroll
+    for (int i = 0; i < NM; i++) {
+        if (i == K) continue;
+        const R c = T[i][K];
+#pragma unroll
+        for (int j = 0; j < NM; j++) if (j != K) T[i][j] -= c * rk[j];
+        T[i][K] = c * p;
+    }
+#pragma unroll
+    for (int j = 0; j < NM; j++) if (j != K) T[K][j] = -rk[j];
+    T[K][K] = p;
+    return true;
+}
+
+template <typename R, int NM>
+DEVI bool lcp_ppt(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg,
+                  const uint8_t* hin = nullptr, uint8_t* sout = nullptr) {
+    R T[NM][NM], b[NM], lo[NM], hi[NM], x[NM], mu[NM], sd[NM];
+    int fi[NM];
+    unsigned cur = 0;   // set the tableau currently represents; 2 bits per row: 0 free, 1 at lo, 2 at hi, 3 fixed at 0
+    unsigned st = 0;    // set to evaluate next
+    const R INF = Num<R>::inf();
+#pragma unroll
+    for (int i = 0; i < NM; i++) {
+        const bool on = i < n;
+        b[i] = on ? bg[i] : (R)0; lo[i] = on ? log_[i] : (R)0; hi[i] = on ? hig[i] : (R)0; fi[i] = on ? fidxg[i] : -1;
+        mu[i] = hi[i];
+        x[i] = 0;
+#pragma unroll
+        for (int j = 0; j < NM; j++) T[i][j] = (on && j < n) ? Ag[i * n + j] : (i == j ? (R)1 : (R)0);
+        sd[i] = Num<R>::sqrt_(T[i][i]);
+        // initial set = the solution of the decoupled (diagonal) problem (see lcp_small)
+        unsigned s = 0, c = 3;
+        if (!on || !(T[i][i] > Num<R>::inert())) s = 3;            // padding / inert row
+        else if (fi[i] >= 0) s = 3;                                  // friction rows wait for stage 2
+        else if (lo[i] == 0 && hi[i] == INF) { s = b[i] > 0 ? 0u : 1u; c = 1; }
+        else if (hi[i] == 0 && lo[i] == -INF) { s = b[i] < 0 ? 0u : 2u; c = 2; }
+        else c = 0;                                                  // two-sided non-friction row: starts free
+        st |= s << (2 * i);
+        cur |= (c == 0 ? 3u : c) << (2 * i);                         // the tableau starts as A itself: every row bound
+    }
+    bool ok = true;
+#pragma unroll 1
+    for (int stage = 0; stage < 2; stage++) {
+        if (stage == 1) {
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                if (fi[i] >= 0 && i < n && T[i][i] > Num<R>::inert()) {   // still bound: T_ii is A_ii's Schur complement > 0
+                    R xn = 0;
+#pragma unroll
+                    for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
+                    const R h = Num<R>::abs_(mu[i] * xn);
+                    hi[i] = h; lo[i] = -h;
+                    st &= ~(3u << (2 * i));
+                    const unsigned hh = hin ? hin[i] : 3u;
+                    if (h == 0) st |= 3u << (2 * i);
+                    else { any = true; if (hh < 3u) st |= hh << (2 * i); }   // hinted set, else free (sticking)
+                }
+            }
+            if (!any) break;
+        }
+        int best = NM + 1, tries = 3;
+        bool done = false;
+#pragma unroll 1
+        for (int it = 0; it < 6 + 3 * NM && !done; it++) {
+            // bring the tableau to the set `st`: one exchange per row whose free/bound status differs
+            unsigned flip = 0;
+#pragma unroll
+            for (int i = 0; i < NM; i++)
+                if ((((st >> (2 * i)) & 3u) == 0) != (((cur >> (2 * i)) & 3u) == 0)) flip |= 1u << i;
+            bool pd = true;
+            static_for<0, NM>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                if ((flip >> k) & 1u) pd = ppt_exchange<k, R, NM>(T) && pd;
+            });
+            if (!pd) { ok = false; break; }
+            cur = st;
+            R z[NM];
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const unsigned si = (st >> (2 * i)) & 3u;
+                z[i] = si == 0 ? b[i] : (si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0));
+            }
+            unsigned nst = st, bad = 0;
+            int nbad = 0;
+            R y[NM], xs = 0, S = 0;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                R s = 0;
+#pragma unroll
+                for (int j = 0; j < NM; j++) s += T[i][j] * z[j];
+                y[i] = s;
+                x[i] = ((st >> (2 * i)) & 3u) == 0 ? s : z[i];
+                const R ax = Num<R>::abs_(x[i]);
+                xs = ax > xs ? ax : xs;
+                S += sd[i] * ax;
+            }
+            const R tx = Num<R>::lcp_tol() * xs;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const unsigned si = (st >> (2 * i)) & 3u;
+                if (si == 3) continue;
+                if (si == 0) {
+                    if (x[i] < lo[i] - tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
+                    else if (x[i] > hi[i] + tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
+                } else {
+                    const R w = y[i] - b[i];
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
+                    if ((si == 1 && w < -tw) || (si == 2 && w > tw)) {
+                        if (lo[i] < hi[i]) { bad |= 1u << i; nbad++; nst = nst & ~(3u << (2 * i)); }
+                    }
+                }
+            }
+            EMU_COUNT(4, 1);
+            if (nbad == 0) { done = true; break; }
+            if (nbad < best) { best = nbad; tries = 3; st = nst; }
+            else if (tries > 0) { tries--; st = nst; }
+            else {  // Murty: flip only the highest-index infeasible row (finite for P-matrices)
+                const int k = 31 - __clz(bad);
+                st = (st & ~(3u << (2 * k))) | (nst & (3u << (2 * k)));
+            }
+        }
+        if (!done) { ok = false; }
+        if (!ok) break;
+        // one round of iterative refinement against A itself (still in thread-local memory): the
+        // tableau's A_FF^-1 is a Gauss-Jordan inverse, and for the nearly rank-deficient A of several
+        // contacts on one body (regularised by the CFM only) its fp32 residual is ~100x Cholesky's
+        {
+            R r[NM];
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                R s = 0;
+                if (i < n && ((st >> (2 * i)) & 3u) == 0) {
+                    s = b[i];
+#pragma unroll
+                    for (int j = 0; j < NM; j++) if (j < n) s -= Ag[i * n + j] * x[j];
+                }
+                r[i] = s;
+            }
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                R s = 0;
+#pragma unroll
+                for (int j = 0; j < NM; j++) s += T[i][j] * r[j];
+                if (((st >> (2 * i)) & 3u) == 0) x[i] += s;
+            }
+        }
+    }
+    if (!ok) { EMU_COUNT(6, 1); return false; }
+#ifdef DARTB_HOST_EMU
+    if (getenv("EMU_LCP_DEBUG")) {
+        printf("ppt<%d,%d> n=%d st=", NM, (int)sizeof(R), n);
+        for (int i = 0; i < n; i++) printf("%u", (st >> (2 * i)) & 3u);
+        printf(" x=");
+        for (int i = 0; i < n; i++) printf(" %.6g", (double)x[i]);
+        printf("\n");
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < NM; i++) if (i < n) { xg[i] = x[i]; if (sout) sout[i] = (uint8_t)((st >> (2 * i)) & 3u); }
+    return true;
+}
+
 // The same block-principal-pivoting iteration for any n <= NR, as loops over thread-local arrays
 // (used above the register sizes; still ~n^3/6 + 3n^2 MACs per iteration and 2-3 iterations per
 // stage, against one fresh factorisation per pivot in the Dantzig loop).
@@ -626,11 +807,20 @@ DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int
     bool ok = false;
     EMU_COUNT(0, 1);
     EMU_HIST(n);
-    if (nmax <= 4) { ok = lcp_small<R, 4>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
-    else if (nmax <= 6 && NR > 4) { ok = lcp_small<R, 6>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
+    // Measured on B200 (gpurun A/B, 4096 Hopper worlds): the tableau form (lcp_ppt) executes fewer
+    // instructions but its per-row exchange branches cost more fetch stalls than they save for a lone
+    // warp per SM (58.6 vs 53.8 us / env step), so the branch-free masked-Cholesky form stays the default.
+#ifdef DARTB_LCP_PPT
+#define LCP_REG lcp_ppt
+#else
+#define LCP_REG lcp_small
+#endif
+    if (nmax <= 4) { ok = LCP_REG<R, 4>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
+    else if (nmax <= 6 && NR > 4) { ok = LCP_REG<R, 6>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (NR > 6) {
-        if (n <= 8) { ok = lcp_small<R, 8>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(2, 1); }
+        if (n <= 8) { ok = LCP_REG<R, 8>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(2, 1); }
     }
+#undef LCP_REG
     if (!ok) {
         if (sout) for (int i = 0; i < n; i++) sout[i] = 3;
         ok = lcp_bpp_local<R, NR>(n, A, x, b, lo, hi, fidx);

@@ -38,6 +38,10 @@ if mode == "variant":
                           ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
             for b in (("32", "128") if n <= 4096 else ("128",)):
                 cfgs.append((env_id, n, b, v))
+elif mode == "main":
+    for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 65536), ("DartWalker2d-v1", 16384),
+                      ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
+        cfgs.append((env_id, n, "32" if n <= 4096 else "128", "0"))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):
