@@ -63,8 +63,9 @@ struct dartb_engine {
     uint64_t* hint = nullptr;                 // LCP warm-start sets, see planar_kernels.cuh::substep
     int32_t* ccount = nullptr; int32_t* cbody = nullptr; float* cdata = nullptr;
     int lcp_mode = 0, pgs_iters = 30, max_episode_steps = 0;
-    int variant_request = -1;                 // -1 auto (DARTB_VARIANT env or static if available), 0, 1
-    int variant = 0;                          // 0 = unrolled static topology, 1 = loop / generic topology
+    int variant_request = -1;                 // -1 auto (DARTB_VARIANT env, else by batch size), 0, 1, 2
+    int variant = 0;                          // 0 = unrolled static topology (one world per thread), 1 = loop / generic
+                                              // topology, 2 = lane-cooperative (8/16 lanes per world, planar_coop.cuh)
     int wpw_request = 0;                      // worlds per warp of k_env_step, 0 = auto (wpw_for)
     int64_t launches = 0;
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
@@ -72,6 +73,9 @@ struct dartb_engine {
     std::string kernel_name;
 };
 
+#ifndef DARTB_COOP_MAX_WORLDS_DEFAULT
+#define DARTB_COOP_MAX_WORLDS_DEFAULT 0   /* auto never picks the cooperative kernel until measured */
+#endif
 static int pick_topo(const std::string& sig, int n_limited) {
     if (sig == TopoHopper::sig && n_limited <= TopoHopper::NL) return TOPO_HOPPER;
     if (sig == TopoWalker::sig && n_limited <= TopoWalker::NL) return TOPO_WALKER;
@@ -97,10 +101,19 @@ static int lower_into(dartb_engine* e) {
     for (int i = 0; i < res.m.nb; i++) nlim += res.m.limited[i] ? 1 : 0;
     int topo = pick_topo(res.signature, nlim);
     if (res.m.ns > LOOP_MAXS || res.m.nb > LOOP_MAXB) return fail("model too large for the planar kernels");
-    static int forced_variant = -1;
-    if (forced_variant < 0) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : 0; }
-    if (topo < 0 || res.m.any_coulomb || e->variant_request == 1 || (e->variant_request < 0 && forced_variant == 1)) e->variant = 1;
-    else e->variant = 0;
+    static int forced_variant = -2;
+    if (forced_variant < -1) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : -1; }
+    const int want = e->variant_request >= 0 ? e->variant_request : forced_variant;
+    if (topo < 0 || res.m.any_coulomb || want == 1) e->variant = 1;
+    else if (want == 2) e->variant = 2;
+    else if (want == 0) e->variant = 0;
+    else {
+        // auto: the cooperative kernel while the batch leaves warp schedulers idle at one world per thread
+        // (it trades ~2.5x more issued instructions per world for ~5x less latency per DART step)
+        static long coop_max = -1;
+        if (coop_max < 0) { const char* ev = getenv("DARTB_COOP_MAX_WORLDS"); coop_max = ev ? atol(ev) : DARTB_COOP_MAX_WORLDS_DEFAULT; }
+        e->variant = (e->n <= coop_max) ? 2 : 0;
+    }
     e->topo = topo;
     e->md = res.m; e->td = res.t;
     lower::convert(res.m, e->mf);
@@ -109,7 +122,7 @@ static int lower_into(dartb_engine* e) {
     e->max_contacts = res.max_contacts;
     e->n_orig_bodies = e->model.n_bodies;
     const char* plane = std::fabs(res.m.en[2]) > 0.5 ? "planar-xy" : (std::fabs(res.m.en[1]) > 0.5 ? "planar-zx" : "planar-yz");
-    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string("/static:") + topo_name(topo)) +
+    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string(e->variant == 2 ? "/coop:" : "/static:") + topo_name(topo)) +
                      (e->f64 ? "/f64" : "/f32");
     return 0;
 }
@@ -193,6 +206,12 @@ static int launch_step(dartb_engine* e, const float* action, float* obs, float* 
                        cudaStream_t st) {
     StepArgs<R> a = make_args<R>(e);
     a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.auto_reset = auto_reset;
+    if (e->variant == 2) {
+        LTab<R>::get(e).step_coop(st, Sel<R>::m(e), Sel<R>::t(e), a);
+        e->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     a.wpw = wpw_for(e);
     const int warps = (e->n + a.wpw - 1) / a.wpw;
     const int bs = block_for(warps * 32), grid = (warps + bs / 32 - 1) / (bs / 32);
@@ -221,7 +240,10 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
     ContactSink<R> sink;
     sink.count = e->ccount; sink.body = e->cbody; sink.data = e->cdata; sink.maxc = e->max_contacts;
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
-    LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
+    if (e->variant == 2 && !fext)
+        LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
+    else
+        LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
     e->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -339,7 +361,7 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             for (int i = 0; i < e->model.n_bodies; i++) e->model.bodies[i].friction_coeff = value;
             return lower_into(e);
         case DARTB_OPT_KERNEL_VARIANT:
-            if (value != 0 && value != 1) return fail("kernel variant must be 0 (unrolled) or 1 (loop)");
+            if (value != 0 && value != 1 && value != 2 && value != -1) return fail("kernel variant must be -1 (auto), 0 (unrolled), 1 (loop) or 2 (lane-cooperative)");
             e->variant_request = (int)value;
             return lower_into(e);
         case DARTB_OPT_WORLDS_PER_WARP:

@@ -29,5 +29,20 @@ static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, in
                       int lcp_mode, int pgs_iters, const ContactSink<R_>& sink) {
     k_substep<T_, R_><<<grid, bs, 0, st>>>(M, n, q, dq, tau, fext, lcp_mode, pgs_iters, sink);
 }
+// lane-cooperative kernels: 4 warps per block, Coop<T>::WPW worlds per warp
+static constexpr int COOP_WARPS = 4;
+static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
+    const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a.n + per_block - 1) / per_block;
+    k_env_step_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a);
+}
+static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, int lcp_mode, int pgs_iters,
+                           const ContactSink<R_>& sink) {
+    const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (n + per_block - 1) / per_block;
+    k_substep_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, 0), st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+}
 #endif
-extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep};
+#ifdef INST_LOOP
+extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, nullptr, nullptr, 0};
+#else
+extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, l_step_coop, l_substep_coop, Coop<T_>::G};
+#endif

@@ -8,28 +8,7 @@
 #include "../../include/dartb.h"
 #include "planar_kernels.cuh"
 #include "planar_loop.cuh"
-
-// ------------------------------------------------------------------------ kernel arguments
-template <typename R>
-struct StepArgs {
-    int n;
-    R* q;                // [nd][n]
-    R* dq;               // [nd][n]
-    uint32_t* episode;   // [n] reset counter (Philox stream position)
-    int32_t* elapsed;    // [n] env steps since reset (TimeLimit)
-    uint8_t* truncated;  // [n]
-    uint64_t* hint;      // [n] LCP active-set warm start (2 bits per constraint slot), all ones = none
-    const float* action; // [n, n_act]
-    float* obs;          // [n, n_obs]
-    float* reward;       // [n]
-    uint8_t* done;       // [n]
-    const uint8_t* mask; // reset mask (k_reset) or null
-    int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
-    int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for
-    uint64_t seed;
-    int64_t world_offset;
-    ContactSink<R> sink;
-};
+#include "planar_coop.cuh"
 
 template <class T, typename R>
 DEVI void write_obs(const PModel<R>& M, const PTask<R>& K, const R (&q)[T::NB], const R (&dq)[T::NB], float* so) {
@@ -470,6 +449,11 @@ struct Launchers {
     void (*reset)(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
     void (*substep)(int grid, int bs, cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, const R* fext,
                     int lcp_mode, int pgs_iters, const ContactSink<R>& sink);
+    // lane-cooperative kernels (planar_coop.cuh); null for the loop variant.  They size their own grid.
+    void (*step_coop)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
+    void (*substep_coop)(cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, int lcp_mode, int pgs_iters,
+                         const ContactSink<R>& sink);
+    int coop_lanes;   // lanes per world of the cooperative kernels (0: none)
 };
 #define DARTB_DECLARE_LAUNCHERS(SUFFIX, R) extern const Launchers<R> dartb_launchers_##SUFFIX;
 DARTB_DECLARE_LAUNCHERS(hopper_f, float)

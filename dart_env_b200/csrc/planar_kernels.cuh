@@ -857,6 +857,28 @@ struct ContactSink {      // where the LAST sub-step's contacts go (dartb_get_co
     int maxc;
 };
 
+// ------------------------------------------------------------------------ kernel arguments
+template <typename R>
+struct StepArgs {
+    int n;
+    R* q;                // [nd][n]
+    R* dq;               // [nd][n]
+    uint32_t* episode;   // [n] reset counter (Philox stream position)
+    int32_t* elapsed;    // [n] env steps since reset (TimeLimit)
+    uint8_t* truncated;  // [n]
+    uint64_t* hint;      // [n] LCP active-set warm start (2 bits per constraint slot), all ones = none
+    const float* action; // [n, n_act]
+    float* obs;          // [n, n_obs]
+    float* reward;       // [n]
+    uint8_t* done;       // [n]
+    const uint8_t* mask; // reset mask (k_reset) or null
+    int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
+    int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for
+    uint64_t seed;
+    int64_t world_offset;
+    ContactSink<R> sink;
+};
+
 // ------------------------------------------------------------------------ kinematics only
 // positions/orientations for the task layer (height of a body COM)
 template <class T, typename R>

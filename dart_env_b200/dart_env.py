@@ -38,7 +38,7 @@ class DartEnv:
                  task: Optional[Task] = None, num_envs: int = 1, batched: Optional[bool] = None, output: str = "torch",
                  device: int = 0, seed: Optional[int] = None, world_offset: int = 0, auto_reset: Optional[bool] = None,
                  max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False,
-                 collidable: bool = True, copy: bool = True):
+                 collidable: bool = True, copy: bool = True, kernel_variant: Optional[int] = None):
         assert obs_type in ("parameter", "image")
         assert action_type in ("continuous", "discrete")
         if obs_type == "image":
@@ -87,6 +87,7 @@ class DartEnv:
         self.perturb_force = None
         self._device_index = device
         self._f64 = f64
+        self._kernel_variant = kernel_variant
 
         self.action_space = Box(np.asarray(action_bounds[1], dtype=np.float64), np.asarray(action_bounds[0], dtype=np.float64))
         high = np.inf * np.ones(self.obs_dim)
@@ -107,7 +108,7 @@ class DartEnv:
         if self.engine is not None:
             self.engine.close()
         self.engine = Engine(self.model, self.task, self.num_envs, device=self._device_index, seed=self._seed_value,
-                             world_offset=self.world_offset, f64=self._f64)
+                             world_offset=self.world_offset, f64=self._f64, kernel_variant=self._kernel_variant)
         if getattr(self, "max_episode_steps", 0):
             self.engine.set_max_episode_steps(self.max_episode_steps)
         dev, n = self.engine.device, self.num_envs

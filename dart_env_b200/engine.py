@@ -12,6 +12,7 @@ from .cstructs import (OPT_FRICTION_ALL, OPT_LCP_MODE, OPT_PGS_ITERS, Task, pack
 from .skel import Model
 
 OPT_MAX_EPISODE_STEPS = 4
+OPT_KERNEL_VARIANT = 5   # -1 auto, 0 one world per thread, 1 loop / generic, 2 lane-cooperative
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -22,7 +23,7 @@ class Engine:
     """N worlds of one skeleton on one GPU (one dartb handle)."""
 
     def __init__(self, model: Model, task: Task, num_worlds: int, device: int = 0, seed: int = 0,
-                 world_offset: int = 0, f64: bool = False):
+                 world_offset: int = 0, f64: bool = False, kernel_variant: Optional[int] = None):
         if not torch.cuda.is_available():
             raise capi.DartbError("no CUDA device: the B200 engine has no CPU fallback")
         self.L = capi.load()
@@ -37,6 +38,8 @@ class Engine:
         capi.check(create(C.byref(self._cm), C.byref(self._ct), self.n, device, seed, world_offset, C.byref(h)))
         self.h = h
         self.max_contacts = self.L.dartb_max_contacts(self.h)
+        if kernel_variant is not None:
+            self.set_option(OPT_KERNEL_VARIANT, kernel_variant)
 
     def close(self):
         if getattr(self, "h", None):

@@ -42,6 +42,12 @@ elif mode == "main":
     for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 65536), ("DartWalker2d-v1", 16384),
                       ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
         cfgs.append((env_id, n, "32" if n <= 4096 else "128", "0"))
+elif mode == "coop":   # per-thread (0) vs lane-cooperative (2) kernels across batch sizes
+    for env_id, sizes in (("DartHopper-v1", (1024, 4096, 16384, 65536)), ("DartWalker2d-v1", (4096, 16384)),
+                          ("DartHalfCheetah-v1", (4096, 16384)), ("DartSnake7Link-v1", (4096, 32768))):
+        for n in sizes:
+            for v in ("0", "2"):
+                cfgs.append((env_id, n, "32" if n <= 4096 else "128", v))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):

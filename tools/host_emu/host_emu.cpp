@@ -8,6 +8,8 @@
 #include "../../dart_env_b200/csrc/lower.h"
 #include "../../dart_env_b200/csrc/planar_kernels.cuh"
 #include "../../dart_env_b200/csrc/planar_loop.cuh"
+#include "simt.h"
+#include "../../dart_env_b200/csrc/planar_coop.cuh"
 
 template <class T, typename R>
 static void run_substep(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
@@ -67,6 +69,28 @@ static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, cons
     }
 }
 
+// the lane-cooperative kernel (planar_coop.cuh) under the one-warp SIMT emulator of simt.h
+template <class T, typename R>
+static void run_substep_coop(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
+                             int lcp_mode, int pgs_iters, double* q_out, double* dq_out, int32_t* count, int32_t* body,
+                             float* data, int maxc) {
+    constexpr int NB = T::NB;
+    std::vector<R> qs((size_t)NB * n), dqs((size_t)NB * n), tau((size_t)NB * n);
+    for (int w = 0; w < n; w++)
+        for (int i = 0; i < NB; i++) {
+            qs[(size_t)i * n + w] = (R)q_in[w * NB + i]; dqs[(size_t)i * n + w] = (R)dq_in[w * NB + i];
+            tau[(size_t)w * NB + i] = tau_in ? (R)tau_in[w * NB + i] : (R)0;
+        }
+    ContactSink<R> sink;
+    sink.count = count; sink.body = body; sink.data = data; sink.maxc = maxc;
+    const int grid = (n + Coop<T>::WPW - 1) / Coop<T>::WPW;
+    simt::launch(grid, coop_shared_bytes<T, R>(1, 0), [&] {
+        k_substep_coop<T, R>(M, n, qs.data(), dqs.data(), tau.data(), lcp_mode, pgs_iters, sink);
+    });
+    for (int w = 0; w < n; w++)
+        for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)qs[(size_t)i * n + w]; dq_out[w * NB + i] = (double)dqs[(size_t)i * n + w]; }
+}
+
 long g_emu_counters[8];
 long g_emu_hist[32];
 extern "C" void emu_hist(long* out, int reset) { for (int i = 0; i < 32; i++) { out[i] = g_emu_hist[i]; if (reset) g_emu_hist[i] = 0; } }
@@ -91,6 +115,14 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
         else run_substep_loop<float>(mf, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);
         return 0;
     }
+#define RUNC(T)                                                                                                         \
+    if (variant == 2 && res.signature == T::sig) {                                                                       \
+        if (fext) { g_err = "the cooperative kernel takes no external forces"; return 1; }                              \
+        if (f64) run_substep_coop<T, double>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
+        else run_substep_coop<T, float>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);          \
+        return 0;                                                                                                        \
+    }
+    RUNC(TopoHopper) RUNC(TopoWalker) RUNC(TopoCheetah) RUNC(TopoSnake)
 #define RUN(T)                                                                                                          \
     if (res.signature == T::sig) {                                                                                       \
         if (f64) run_substep<T, double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, hints); \
