@@ -59,10 +59,20 @@ def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
             defs += ["-DINST_LOOP=1"] if topo is None else ["-DINST_TOPO=%s" % topo]
             obj = os.path.join(OBJ, "inst_%s_%s.o" % (name, sfx))
             jobs_list.append((obj, [nvcc] + ARCH + COMMON + ptxas + defs + ["-c", os.path.join(CSRC, "inst.cu")]))
+    only = os.environ.get("DARTB_BUILD_ONLY")   # developer shortcut: "hopper_f,dartb" recompiles just those objects
+    if only:
+        keep = set(only.split(","))
+        jobs_all = jobs_list
+        jobs_list = [j for j in jobs_list if any(os.path.basename(j[0]) in ("inst_%s.o" % k, "%s.o" % k) for k in keep)]
+        missing = [j[0] for j in jobs_all if j not in jobs_list and not os.path.exists(j[0])]
+        if missing:
+            raise RuntimeError("DARTB_BUILD_ONLY needs the other objects to exist: %s" % missing)
+    else:
+        jobs_all = jobs_list
     nj = jobs or min(len(jobs_list), os.cpu_count() or 4)
     with ThreadPoolExecutor(nj) as ex:
         logs = list(ex.map(lambda j: _run(j[1] + ["-o", j[0]], verbose), jobs_list))
-    log = _run([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", SO] + [j[0] for j in jobs_list], verbose)
+    log = _run([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", SO] + [j[0] for j in jobs_all], verbose)
     if verbose:
         sys.stderr.write("".join(logs) + log)
     return SO

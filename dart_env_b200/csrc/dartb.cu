@@ -67,6 +67,7 @@ struct dartb_engine {
     int variant = 0;                          // 0 = unrolled static topology (one world per thread), 1 = loop / generic
                                               // topology, 2 = lane-cooperative (8/16 lanes per world, planar_coop.cuh)
     int wpw_request = 0;                      // worlds per warp of k_env_step, 0 = auto (wpw_for)
+    void* coop_tab = nullptr; size_t coop_tab_bytes = 0; bool coop_tab_dirty = true;   // per-lane constants of the cooperative kernels
     int64_t launches = 0;
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
     float* h_stage = nullptr; float* d_stage = nullptr; float* h_stage_dev = nullptr; size_t stage_floats = 0;
@@ -115,6 +116,7 @@ static int lower_into(dartb_engine* e) {
         e->variant = (e->n <= coop_max) ? 2 : 0;
     }
     e->topo = topo;
+    e->coop_tab_dirty = true;
     e->md = res.m; e->td = res.t;
     lower::convert(res.m, e->mf);
     lower::convert(res.t, e->tf);
@@ -201,13 +203,34 @@ template <> struct LTab<double> {
     }
 };
 
+// (re)upload the per-lane constant table of the cooperative kernels after the model was (re)lowered
+template <typename R>
+static int coop_table_sync(dartb_engine* e, cudaStream_t st) {
+    if (!e->coop_tab_dirty) return 0;
+    const Launchers<R>& L = LTab<R>::get(e);
+    if (!L.coop_table) return fail("this topology has no cooperative kernel");
+    if (e->coop_tab_bytes < L.coop_table_bytes) {
+        if (e->coop_tab) cudaFree(e->coop_tab);
+        e->coop_tab = nullptr; e->coop_tab_bytes = 0;
+        CK(cudaMalloc(&e->coop_tab, L.coop_table_bytes));
+        e->coop_tab_bytes = L.coop_table_bytes;
+    }
+    std::vector<unsigned char> host(L.coop_table_bytes);
+    L.coop_table(Sel<R>::m(e), Sel<R>::t(e), host.data());
+    CK(cudaStreamSynchronize(st));   // a previous launch may still be reading the old table
+    CK(cudaMemcpy(e->coop_tab, host.data(), host.size(), cudaMemcpyHostToDevice));
+    e->coop_tab_dirty = false;
+    return 0;
+}
+
 template <typename R>
 static int launch_step(dartb_engine* e, const float* action, float* obs, float* reward, uint8_t* done, int auto_reset,
                        cudaStream_t st) {
     StepArgs<R> a = make_args<R>(e);
     a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.auto_reset = auto_reset;
     if (e->variant == 2) {
-        LTab<R>::get(e).step_coop(st, Sel<R>::m(e), Sel<R>::t(e), a);
+        if (coop_table_sync<R>(e, st)) return 1;
+        LTab<R>::get(e).step_coop(st, Sel<R>::m(e), Sel<R>::t(e), a, e->coop_tab);
         e->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -240,8 +263,10 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
     ContactSink<R> sink;
     sink.count = e->ccount; sink.body = e->cbody; sink.data = e->cdata; sink.maxc = e->max_contacts;
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
-    if (e->variant == 2 && !fext)
-        LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
+    if (e->variant == 2 && !fext) {
+        if (coop_table_sync<R>(e, st)) return 1;
+        LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->coop_tab, e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
+    }
     else
         LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
     e->launches++;
@@ -342,6 +367,7 @@ int dartb_destroy(dartb_handle_t e) {
     DeviceGuard g(e->device);
     cudaFree(e->q); cudaFree(e->dq); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
     cudaFree(e->truncated); cudaFree(e->hint); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
+    if (e->coop_tab) cudaFree(e->coop_tab);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->d_stage) cudaFree(e->d_stage);
     delete e;

@@ -31,18 +31,22 @@ static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, in
 }
 // lane-cooperative kernels: 4 warps per block, Coop<T>::WPW worlds per warp
 static constexpr int COOP_WARPS = 4;
-static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
+static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a, const void* tab) {
     const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a.n + per_block - 1) / per_block;
-    k_env_step_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a);
+    const CoopLane<T_, R_>* t = (const CoopLane<T_, R_>*)tab;
+    if (K.fluid_force) k_env_step_coop<T_, R_, true><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
+    else k_env_step_coop<T_, R_, false><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
 }
-static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, int lcp_mode, int pgs_iters,
-                           const ContactSink<R_>& sink) {
+static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, const void* tab, int n, R_* q, R_* dq, const R_* tau, int lcp_mode,
+                           int pgs_iters, const ContactSink<R_>& sink) {
     const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (n + per_block - 1) / per_block;
-    k_substep_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, 0), st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+    k_substep_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, 0), st>>>(M, (const CoopLane<T_, R_>*)tab, n, q, dq, tau,
+                                                                                                    lcp_mode, pgs_iters, sink);
 }
+static void l_coop_table(const PModel<R_>& M, const PTask<R_>& K, void* out) { coop_build_table<T_, R_>(M, &K, (CoopLane<T_, R_>*)out); }
 #endif
 #ifdef INST_LOOP
-extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, nullptr, nullptr, 0};
+extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, nullptr, nullptr, nullptr, 0, 0};
 #else
-extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, l_step_coop, l_substep_coop, Coop<T_>::G};
+extern const Launchers<R_> CAT2(dartb_launchers_, INST_SUFFIX) = {l_step, l_reset, l_substep, l_step_coop, l_substep_coop, l_coop_table, sizeof(CoopLane<T_, R_>) * Coop<T_>::G, Coop<T_>::G};
 #endif

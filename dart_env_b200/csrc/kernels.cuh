@@ -450,9 +450,11 @@ struct Launchers {
     void (*substep)(int grid, int bs, cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, const R* fext,
                     int lcp_mode, int pgs_iters, const ContactSink<R>& sink);
     // lane-cooperative kernels (planar_coop.cuh); null for the loop variant.  They size their own grid.
-    void (*step_coop)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
-    void (*substep_coop)(cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, int lcp_mode, int pgs_iters,
-                         const ContactSink<R>& sink);
+    void (*step_coop)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a, const void* lane_table);
+    void (*substep_coop)(cudaStream_t st, const PModel<R>& M, const void* lane_table, int n, R* q, R* dq, const R* tau, int lcp_mode,
+                         int pgs_iters, const ContactSink<R>& sink);
+    void (*coop_table)(const PModel<R>& M, const PTask<R>& K, void* host_out);   // fills coop_table_bytes of per-lane constants
+    size_t coop_table_bytes;
     int coop_lanes;   // lanes per world of the cooperative kernels (0: none)
 };
 #define DARTB_DECLARE_LAUNCHERS(SUFFIX, R) extern const Launchers<R> dartb_launchers_##SUFFIX;

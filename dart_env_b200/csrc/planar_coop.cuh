@@ -48,11 +48,13 @@ struct Coop {
     __host__ __device__ static constexpr bool anc(int j, int i) { return topo_is_ancestor<T>(j, i); }   // j == i or j above i
 };
 
-// per-lane constants (lane l of a group: body l, dof l, capsule l), loaded once per kernel
+// per-lane constants (lane l of a group: body l, dof l, capsule l, actuator of dof l).  A table of
+// G of these is built on the HOST (coop_lane_init) and kept in device memory; each lane loads its
+// entry once per kernel with a few vector loads instead of a per-field select chain.
 template <class T, typename R>
-struct CoopLane {
+struct alignas(16) CoopLane {
     int l;
-    bool isb, iss;
+    int isb, iss;
     int par, hop2, hop4, hop8;
     unsigned anc, desc;
     int jt, limited;
@@ -60,37 +62,36 @@ struct CoopLane {
     int sb, sorig;
     unsigned sanc;
     R scx, scy, sdx, sdy, shalf, srad, smu;
+    int act, pen_dof;          // task layer: actuator index driving this dof (-1: none); limit-penalty dof flag
+    R ascale, alo, ahi;
 };
 
 template <class T, typename R>
-DEVI void coop_lane_init(const PModel<R>& M, int l, CoopLane<T, R>& c) {
+inline void coop_lane_init(const PModel<R>& M, const PTask<R>* K, int l, CoopLane<T, R>& c) {   // HOST: builds table entry l
     using C = Coop<T>;
+    c = CoopLane<T, R>();
     c.l = l; c.isb = l < C::NB; c.iss = l < C::NS;
-    c.par = -1; c.hop2 = -1; c.hop4 = -1; c.hop8 = -1; c.anc = 0; c.desc = 0; c.jt = 0; c.limited = 0;
-    c.sgn = 0; c.ax = 0; c.ay = 0; c.ux = 0; c.uy = 0; c.mass = 0; c.cx = 0; c.cy = 0; c.izz = 0; c.damp = 0; c.ksp = 0;
-    c.rest = 0; c.qlo = 0; c.qhi = 0; c.ox = 0; c.oy = 0; c.fnx = 0; c.fny = 0; c.qinit = 0; c.dqinit = 0;
-    c.sb = 0; c.sorig = -1; c.sanc = 0; c.scx = 0; c.scy = 0; c.sdx = 0; c.sdy = 0; c.shalf = 0; c.srad = 0; c.smu = 0;
-    static_for<0, C::NB>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        if (l == i) {
-            c.par = T::parent(i); c.hop2 = C::hop(i, 2); c.hop4 = C::hop(i, 4); c.hop8 = C::hop(i, 8);
-            c.anc = C::ancmask(i); c.desc = C::descmask(i); c.jt = T::jtype(i); c.limited = M.limited[i];
-            c.sgn = M.sgn[i]; c.ax = M.ax[i]; c.ay = M.ay[i]; c.ux = M.ux[i]; c.uy = M.uy[i];
-            c.mass = M.mass[i]; c.cx = M.cx[i]; c.cy = M.cy[i]; c.izz = M.izz[i];
-            c.damp = M.damping[i]; c.ksp = M.kspring[i]; c.rest = M.rest[i]; c.qlo = M.qlo[i]; c.qhi = M.qhi[i];
-            c.ox = M.ox[i]; c.oy = M.oy[i]; c.fnx = M.fnx[i]; c.fny = M.fny[i]; c.qinit = M.qinit[i]; c.dqinit = M.dqinit[i];
-        }
-    });
-    if constexpr (C::NS > 0) {
-        static_for<0, C::NS>([&](auto sc) {
-            constexpr int s = decltype(sc)::value;
-            if (l == s) {
-                c.sb = T::sbody(s); c.sanc = C::ancmask(T::sbody(s)); c.sorig = M.sorig[s];
-                c.scx = M.scx[s]; c.scy = M.scy[s]; c.sdx = M.sdx[s]; c.sdy = M.sdy[s];
-                c.shalf = M.shalf[s]; c.srad = M.srad[s]; c.smu = M.smu[s];
-            }
-        });
+    c.par = -1; c.hop2 = -1; c.hop4 = -1; c.hop8 = -1; c.sorig = -1; c.act = -1;
+    if (l < C::NB) {
+        const int i = l;
+        c.par = T::parent(i); c.hop2 = C::hop(i, 2); c.hop4 = C::hop(i, 4); c.hop8 = C::hop(i, 8);
+        c.anc = C::ancmask(i); c.desc = C::descmask(i); c.jt = T::jtype(i); c.limited = M.limited[i];
+        c.sgn = M.sgn[i]; c.ax = M.ax[i]; c.ay = M.ay[i]; c.ux = M.ux[i]; c.uy = M.uy[i];
+        c.mass = M.mass[i]; c.cx = M.cx[i]; c.cy = M.cy[i]; c.izz = M.izz[i];
+        c.damp = M.damping[i]; c.ksp = M.kspring[i]; c.rest = M.rest[i]; c.qlo = M.qlo[i]; c.qhi = M.qhi[i];
+        c.ox = M.ox[i]; c.oy = M.oy[i]; c.fnx = M.fnx[i]; c.fny = M.fny[i]; c.qinit = M.qinit[i]; c.dqinit = M.dqinit[i];
+        if (K) { c.act = K->dof_act[i]; c.ascale = K->dof_scale[i]; c.alo = K->dof_lo[i]; c.ahi = K->dof_hi[i]; c.pen_dof = K->limit_pen_dof == i; }
     }
+    if (l < C::NS) {
+        const int s = l;
+        c.sb = T::sbody(s); c.sanc = C::ancmask(T::sbody(s)); c.sorig = M.sorig[s];
+        c.scx = M.scx[s]; c.scy = M.scy[s]; c.sdx = M.sdx[s]; c.sdy = M.sdy[s];
+        c.shalf = M.shalf[s]; c.srad = M.srad[s]; c.smu = M.smu[s];
+    }
+}
+template <class T, typename R>
+inline void coop_build_table(const PModel<R>& M, const PTask<R>* K, CoopLane<T, R>* out /*[Coop<T>::G]*/) {
+    for (int l = 0; l < Coop<T>::G; l++) coop_lane_init<T, R>(M, K, l, out[l]);
 }
 
 // ------------------------------------------------------------------------ group collectives
@@ -604,12 +605,16 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
             }
             ltl_solve_t<T, RM>(Mf, Li, Y[h]);     // Y_r = L^-T J_r^T
         }
-        // A[r][s] = Y_r . Y_s (+ CFM on the diagonal)
+        // A[r][s] = Y_r . Y_s (+ CFM on the diagonal).  The smallest class keeps every Y_s it fetched, so K7
+        // needs the impulses only (NC shuffles) instead of a NB-vector reduction over the group.
+        constexpr bool KEEPY = NCx <= 4;
+        RM Yall[KEEPY ? NC : 1][NB];
         R A[RPL][NC];
 #pragma unroll
         for (int s = 0; s < NC; s++) {
             RM Ys[NB];
             static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Ys[j] = gshfl<G>(Y[s / G][j], s % G); });
+            if constexpr (KEEPY) { static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Yall[s][j] = Ys[j]; }); }
 #pragma unroll
             for (int h = 0; h < RPL; h++) {
                 RM v = 0;
@@ -645,13 +650,25 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         }
         // ---------------- K7: dq += L^-1 sum_r Y_r x_r
         RM zs[NB];
-        static_for<0, NB>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            RM v = 0;
+        if constexpr (KEEPY) {
+            R xs_[NC];
+            CoopLcp<T, R, NCx>::gather_rows(x, xs_, nmax);
+            static_for<0, NB>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                RM v = 0;
 #pragma unroll
-            for (int h = 0; h < RPL; h++) if (l + h * G < n) v += Y[h][j] * (RM)x[h];
-            zs[j] = group_sum<G>(v);
-        });
+                for (int s = 0; s < NC; s++) v += Yall[s][j] * (RM)xs_[s];
+                zs[j] = v;
+            });
+        } else {
+            static_for<0, NB>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                RM v = 0;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) if (l + h * G < n) v += Y[h][j] * (RM)x[h];
+                zs[j] = group_sum<G>(v);
+            });
+        }
         ltl_solve<T, RM>(Mf, Li, zs);
         static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; if (l == i) dq += (R)zs[i]; });
         // stick/slide sets of the friction rows for the next step
@@ -764,24 +781,25 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
     // in ddq where the articulated-body recursion loses ~1e-6.  The composite inertias, M, its factor and
     // the solves are therefore carried in RM = fp64 (exact for the fp32 kinematics they are built from,
     // i.e. the mass matrix of a 1e-7-perturbed pose); everything else stays in R.
-    RM Jc = 0, hxc = 0, hyc = 0, mc = 0, nc_ = 0, fxc = 0, fyc = 0;
+    RM Jc = 0, hxc = 0, hyc = 0, mc = 0;
+    R nc_ = 0, fxc = 0, fyc = 0;   // the bias wrench needs no more than R (measured: no loss on the goldens)
     R Pgx[NB], Pgy[NB];
     {
-        const R g0 = c.isb ? c.izz : (R)0, g1 = c.isb ? m : (R)0, g4 = c.isb ? Fx : (R)0, g5 = c.isb ? Fy : (R)0;
+        const R g4 = c.isb ? Fx : (R)0, g5 = c.isb ? Fy : (R)0;
         static_for<0, NB>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            const R izz_j = gshfl<G>(g0, j), m_j = gshfl<G>(g1, j), Dx_j = gshfl<G>(Dx, j), Dy_j = gshfl<G>(Dy, j);
-            const R Fx_j = gshfl<G>(g4, j), Fy_j = gshfl<G>(g5, j), nF_j = FLUID ? gshfl<G>(nF, j) : (R)0;
+            const R Dx_j = gshfl<G>(Dx, j), Dy_j = gshfl<G>(Dy, j), Fx_j = gshfl<G>(g4, j), Fy_j = gshfl<G>(g5, j);
+            const R nF_j = FLUID ? gshfl<G>(nF, j) : (R)0;
             Pgx[j] = gshfl<G>(Px, j); Pgy[j] = gshfl<G>(Py, j);
-            if ((c.desc >> j) & 1u) {
-                const RM ex = (RM)Dx_j - (RM)Px, ey = (RM)Dy_j - (RM)Py, mj = (RM)m_j;
-                Jc += (RM)izz_j + mj * (ex * ex + ey * ey); hxc += -mj * ey; hyc += mj * ex; mc += mj;
-#ifdef DARTB_COOP_BIAS_FLOAT
-                nc_ = (RM)((R)nc_ + ((R)ex * Fy_j - (R)ey * Fx_j + nF_j)); fxc = (RM)((R)fxc + Fx_j); fyc = (RM)((R)fyc + Fy_j);
-#else
-                nc_ += ex * (RM)Fy_j - ey * (RM)Fx_j + (RM)nF_j; fxc += (RM)Fx_j; fyc += (RM)Fy_j;
-#endif
-            }
+            const bool in = (c.desc >> j) & 1u;             // body j hangs below this joint
+            // its COM seen from this joint's origin: the difference is formed in RM, where it is EXACT, so all
+            // rows of M describe one and the same (1e-7-perturbed) geometry
+            const RM ex = (RM)Dx_j - (RM)Px, ey = (RM)Dy_j - (RM)Py;
+            const R exf = (R)ex, eyf = (R)ey;
+            const RM mj = in ? (RM)M.mass[j] : (RM)0, izj = in ? (RM)M.izz[j] : (RM)0;
+            Jc += izj + mj * (ex * ex + ey * ey); hxc -= mj * ey; hyc += mj * ex; mc += mj;
+            const R fxm = in ? Fx_j : (R)0, fym = in ? Fy_j : (R)0;
+            nc_ += exf * fym - eyf * fxm + (in ? nF_j : (R)0); fxc += fxm; fyc += fym;
         });
     }
     // prismatic axes of the ancestors (static joint types: only prismatic bodies are fetched)
@@ -792,9 +810,10 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
         else { Ugx[j] = 0; Ugy[j] = 0; }
     });
     // bias force and F_i = Ic_i S_i, both about this joint's origin
-    RM cb, F0, F1, F2;
-    if (rev) { cb = (RM)c.sgn * nc_; F0 = (RM)c.sgn * Jc; F1 = (RM)c.sgn * hxc; F2 = (RM)c.sgn * hyc; }
-    else { cb = (RM)uwx * fxc + (RM)uwy * fyc; F0 = hxc * (RM)uwx + hyc * (RM)uwy; F1 = mc * (RM)uwx; F2 = mc * (RM)uwy; }
+    RM F0, F1, F2;
+    R cb;
+    if (rev) { cb = c.sgn * nc_; F0 = (RM)c.sgn * Jc; F1 = (RM)c.sgn * hxc; F2 = (RM)c.sgn * hyc; }
+    else { cb = uwx * fxc + uwy * fyc; F0 = hxc * (RM)uwx + hyc * (RM)uwy; F1 = mc * (RM)uwx; F2 = mc * (RM)uwy; }
     // own row of M: M_ij = S_j(at this origin) . F_i for the ancestors j
     RM Mrow[NB];
     static_for<0, NB>([&](auto jc) {
@@ -802,16 +821,25 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
         if constexpr (T::jtype(j) == PM_REV) Mrow[j] = (RM)M.sgn[j] * (F0 + ((RM)Pgy[j] - (RM)Py) * F1 - ((RM)Pgx[j] - (RM)Px) * F2);
         else Mrow[j] = (RM)Ugx[j] * F1 + (RM)Ugy[j] * F2;
     });
+    // every lane assembles the full (tree-sparse) M from the rows
+    RM Mf[NB][NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        static_for<0, i + 1>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (C::anc(j, i)) Mf[i][j] = gshfl<G>(Mrow[j], i);
+        });
+    });
     // ---------------- K3: (M + dt D + dt^2 K) ddq = tau - c - K (q - rest + dt dq) - D dq
     {
-        const RM rhs = c.isb ? (RM)tau - cb - (RM)(c.ksp * (q - c.rest + dt * dq)) - (RM)(c.damp * dq) : (RM)0;
+        const R rhs = c.isb ? tau - cb - c.ksp * (q - c.rest + dt * dq) - c.damp * dq : (R)0;
         RM xg[NB], Mt[NB][NB], Li[NB];
         static_for<0, NB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            xg[i] = gshfl<G>(rhs, i);
+            xg[i] = (RM)gshfl<G>(rhs, i);
             static_for<0, i + 1>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                if constexpr (C::anc(j, i)) Mt[i][j] = gshfl<G>(Mrow[j], i);   // every lane assembles the full (tree-sparse) M
+                if constexpr (C::anc(j, i)) Mt[i][j] = Mf[i][j];
             });
             Mt[i][i] += (RM)dt * (RM)M.damping[i] + (RM)dt * (RM)dt * (RM)M.kspring[i];
         });
@@ -868,19 +896,8 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
     const int nmax = coop_warp_max(n);
     if (nmax > 0) {
         // plain M = L^T L for the impulse tests (DART uses the non-implicit articulated inertia there)
-#ifdef DARTB_COOP_RC_FLOAT
-        using RC = R;
-#else
         using RC = RM;
-#endif
-        RC Mf[NB][NB], Li[NB];
-        static_for<0, NB>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            static_for<0, i + 1>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                if constexpr (C::anc(j, i)) Mf[i][j] = gshfl<G>((RC)Mrow[j], i);
-            });
-        });
+        RC Li[NB];
         ltl_factor<T, RC, FASTM>(Mf, Li);
         CoopContact<R> ct;
         ct.hasc = hasc; ct.fric = fric; ct.Px = cPx; ct.Py = cPy; ct.nx = cnx; ct.ny = cny; ct.depth = cdepth; ct.mu = cmu;
@@ -924,8 +941,8 @@ __host__ __device__ constexpr size_t coop_shared_bytes(int warps, int n_obs) {
 
 // exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175), no external forces
 template <class T, typename R>
-COOP_GLOBAL void k_substep_coop(const COOP_GRID_CONSTANT PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, int lcp_mode,
-                                int pgs_iters, const COOP_GRID_CONSTANT ContactSink<R> sink) {
+COOP_GLOBAL void k_substep_coop(const COOP_GRID_CONSTANT PModel<R> M, const CoopLane<T, R>* tab, int n, R* qs, R* dqs,
+                                const R* tau_in /*[n,nd]*/, int lcp_mode, int pgs_iters, const COOP_GRID_CONSTANT ContactSink<R> sink) {
     using C = Coop<T>;
     constexpr int G = C::G, NB = C::NB;
     COOP_SHARED_BYTES(smraw);
@@ -934,8 +951,7 @@ COOP_GLOBAL void k_substep_coop(const COOP_GRID_CONSTANT PModel<R> M, int n, R* 
     const int w = (blockIdx.x * nwarps + warp) * C::WPW + gi;
     const bool wactive = w < n;
     CoopRows<T, R>* rows = reinterpret_cast<CoopRows<T, R>*>(smraw) + (warp * C::WPW + gi);
-    CoopLane<T, R> c;
-    coop_lane_init<T, R>(M, l, c);
+    const CoopLane<T, R> c = tab[l];
     const bool mine = wactive && c.isb;
     R q = mine ? qs[(size_t)l * n + w] : c.qinit, dq = mine ? dqs[(size_t)l * n + w] : (R)0;
     const R tau = (mine && tau_in) ? tau_in[(size_t)w * NB + l] : (R)0;
@@ -945,9 +961,9 @@ COOP_GLOBAL void k_substep_coop(const COOP_GRID_CONSTANT PModel<R> M, int n, R* 
 }
 
 // one launch per env.step(): action -> frame_skip DART steps -> obs / reward / done -> masked auto-reset
-template <class T, typename R>
+template <class T, typename R, bool FLUID>
 COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COOP_GRID_CONSTANT PTask<R> K,
-                                 const COOP_GRID_CONSTANT StepArgs<R> a) {
+                                 const COOP_GRID_CONSTANT StepArgs<R> a, const CoopLane<T, R>* tab) {
     using C = Coop<T>;
     constexpr int G = C::G, NB = C::NB, WPW = C::WPW;
     COOP_SHARED_BYTES(smraw);
@@ -958,17 +974,11 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     const bool wactive = w < a.n;
     CoopRows<T, R>* rows = reinterpret_cast<CoopRows<T, R>*>(smraw) + (warp * WPW + gi);
     float* sobs = reinterpret_cast<float*>(smraw + (size_t)nwarps * WPW * sizeof(CoopRows<T, R>)) + (size_t)warp * WPW * K.n_obs;
-    CoopLane<T, R> c;
-    coop_lane_init<T, R>(M, l, c);
+    const CoopLane<T, R> c = tab[l];
     const bool mine = wactive && c.isb;
     // this dof's actuator (hopper.py:24-32: clamp, scale, scatter)
-    int act = -1;
-    R ascale = 0, alo = 0, ahi = 0;
-    int pen_dof = 0;
-    static_for<0, NB>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        if (l == i) { act = K.dof_act[i]; ascale = K.dof_scale[i]; alo = K.dof_lo[i]; ahi = K.dof_hi[i]; pen_dof = K.limit_pen_dof == i; }
-    });
+    const int act = c.act, pen_dof = c.pen_dof;
+    const R ascale = c.ascale, alo = c.alo, ahi = c.ahi;
     R q = mine ? a.q[(size_t)l * a.n + w] : c.qinit, dq = mine ? a.dq[(size_t)l * a.n + w] : (R)0;
     // control cost uses the RAW action, summed in action order
     const R araw = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
@@ -984,10 +994,7 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     uint32_t hint = wactive ? (uint32_t)a.hint[w] : 0xffffffffu;
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (f == K.frame_skip - 1 && (a.sink.count || a.sink.body || a.sink.data)) ? &a.sink : nullptr;
-        if (K.fluid_force)
-            coop_substep<T, R, true>(M, c, gbase, q, dq, tau, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, wactive, w, hint, rows);
-        else
-            coop_substep<T, R, false>(M, c, gbase, q, dq, tau, (R)0, (R)0, a.lcp_mode, a.pgs_iters, sk, wactive, w, hint, rows);
+        coop_substep<T, R, FLUID>(M, c, gbase, q, dq, tau, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, wactive, w, hint, rows);
     }
     // reward / done (hopper.py:36-65, walker2d.py:22-65, half_cheetah.py:40-77, snake_7link.py:68-87)
     const R q0 = gshfl<G>(q, 0), ang = gshfl<G>(q, NB > 2 ? 2 : 0);

@@ -84,8 +84,10 @@ static void run_substep_coop(const PModel<R>& M, int n, const double* q_in, cons
     ContactSink<R> sink;
     sink.count = count; sink.body = body; sink.data = data; sink.maxc = maxc;
     const int grid = (n + Coop<T>::WPW - 1) / Coop<T>::WPW;
+    CoopLane<T, R> tab[Coop<T>::G];
+    coop_build_table<T, R>(M, nullptr, tab);
     simt::launch(grid, coop_shared_bytes<T, R>(1, 0), [&] {
-        k_substep_coop<T, R>(M, n, qs.data(), dqs.data(), tau.data(), lcp_mode, pgs_iters, sink);
+        k_substep_coop<T, R>(M, tab, n, qs.data(), dqs.data(), tau.data(), lcp_mode, pgs_iters, sink);
     });
     for (int w = 0; w < n; w++)
         for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)qs[(size_t)i * n + w]; dq_out[w * NB + i] = (double)dqs[(size_t)i * n + w]; }
