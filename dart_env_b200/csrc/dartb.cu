@@ -74,9 +74,6 @@ struct dartb_engine {
     std::string kernel_name;
 };
 
-#ifndef DARTB_COOP_MAX_WORLDS_DEFAULT
-#define DARTB_COOP_MAX_WORLDS_DEFAULT 0   /* auto never picks the cooperative kernel until measured */
-#endif
 static int pick_topo(const std::string& sig, int n_limited) {
     if (sig == TopoHopper::sig && n_limited <= TopoHopper::NL) return TOPO_HOPPER;
     if (sig == TopoWalker::sig && n_limited <= TopoWalker::NL) return TOPO_WALKER;
@@ -111,9 +108,14 @@ static int lower_into(dartb_engine* e) {
     else {
         // auto: the cooperative kernel while the batch leaves warp schedulers idle at one world per thread
         // (it trades ~2.5x more issued instructions per world for ~5x less latency per DART step)
-        static long coop_max = -1;
-        if (coop_max < 0) { const char* ev = getenv("DARTB_COOP_MAX_WORLDS"); coop_max = ev ? atol(ev) : DARTB_COOP_MAX_WORLDS_DEFAULT; }
-        e->variant = (e->n <= coop_max) ? 2 : 0;
+        // Crossovers measured on B200 (gpurun_out/sweep_coop*.log, us per env step, cooperative vs per-thread):
+        //   Hopper      4096: 38 vs 54    6144: 62 vs 54      Walker2d   4096: 107 vs 135   8192: 196 vs 156
+        //   HalfCheetah 8192: 340 vs 489  12288: 497 vs 492   Snake7Link 2048: 34 vs 39     4096: 59 vs 42
+        static long coop_max = -2;
+        if (coop_max < -1) { const char* ev = getenv("DARTB_COOP_MAX_WORLDS"); coop_max = ev ? atol(ev) : -1; }
+        long lim = coop_max;
+        if (lim < 0) lim = topo == TOPO_HOPPER ? 4736 : (topo == TOPO_WALKER ? 6144 : (topo == TOPO_CHEETAH ? 12288 : 2368));
+        e->variant = (e->n <= lim) ? 2 : 0;
     }
     e->topo = topo;
     e->coop_tab_dirty = true;

@@ -1,5 +1,7 @@
 // inst.cu — one (topology, precision) instantiation of the kernels per translation unit.
 // Compiled by build.py with -DINST_TOPO=<TopoX|LOOP> -DINST_REAL=<float|double> -DINST_SUFFIX=<name>.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 #define CAT2_(a, b) a##b
@@ -30,7 +32,12 @@ static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, in
     k_substep<T_, R_><<<grid, bs, 0, st>>>(M, n, q, dq, tau, fext, lcp_mode, pgs_iters, sink);
 }
 // lane-cooperative kernels: 4 warps per block, Coop<T>::WPW worlds per warp
-static constexpr int COOP_WARPS = 4;
+static int coop_warps() {   // warps per block (1, 2 or 4; DARTB_COOP_WARPS overrides the default)
+    static int v = 0;
+    if (!v) { const char* e = getenv("DARTB_COOP_WARPS"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 4; }
+    return v;
+}
+#define COOP_WARPS coop_warps()
 static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a, const void* tab) {
     const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a.n + per_block - 1) / per_block;
     const CoopLane<T_, R_>* t = (const CoopLane<T_, R_>*)tab;

@@ -94,6 +94,19 @@ inline void coop_build_table(const PModel<R>& M, const PTask<R>* K, CoopLane<T, 
     for (int l = 0; l < Coop<T>::G; l++) coop_lane_init<T, R>(M, K, l, out[l]);
 }
 
+// products / sums that must not be contracted into FMAs (bit-identical results across code paths)
+#ifdef DARTB_HOST_EMU
+static inline double coop_mul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline float coop_mul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline double coop_add_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline float coop_add_rn(float a, float b) { volatile float r = a + b; return r; }
+#else
+DEVI double coop_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+DEVI float coop_mul_rn(float a, float b) { return __fmul_rn(a, b); }
+DEVI double coop_add_rn(double a, double b) { return __dadd_rn(a, b); }
+DEVI float coop_add_rn(float a, float b) { return __fadd_rn(a, b); }
+#endif
+
 // ------------------------------------------------------------------------ group collectives
 template <int G, typename V>
 DEVI V gshfl(V v, int src) { return __shfl_sync(COOP_FULL, v, src, G); }
@@ -106,7 +119,7 @@ DEVI int coop_warp_max(int v) {
 template <int G, typename R>
 DEVI R group_sum(R v) {
 #pragma unroll
-    for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(COOP_FULL, v, m);
+    for (int m = G / 2; m >= 1; m >>= 1) v = coop_add_rn(v, __shfl_xor_sync(COOP_FULL, v, m));
     return v;
 }
 template <int G, typename R>
@@ -653,19 +666,22 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         if constexpr (KEEPY) {
             R xs_[NC];
             CoopLcp<T, R, NCx>::gather_rows(x, xs_, nmax);
+            // summed in the order of the group_sum butterfly of the larger classes (products rounded one by
+            // one, pairs (0,2) and (1,3) first), so a world's result does not depend on which class its warp
+            // neighbours put it in
+            static_assert(NC == 4, "the small class is 4 columns");
             static_for<0, NB>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                RM v = 0;
-#pragma unroll
-                for (int s = 0; s < NC; s++) v += Yall[s][j] * (RM)xs_[s];
-                zs[j] = v;
+                const RM p0 = coop_mul_rn(Yall[0][j], (RM)xs_[0]), p1 = coop_mul_rn(Yall[1][j], (RM)xs_[1]);
+                const RM p2 = coop_mul_rn(Yall[2][j], (RM)xs_[2]), p3 = coop_mul_rn(Yall[3][j], (RM)xs_[3]);
+                zs[j] = coop_add_rn(coop_add_rn(p0, p2), coop_add_rn(p1, p3));
             });
         } else {
             static_for<0, NB>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                RM v = 0;
+                RM v = (l < n) ? coop_mul_rn(Y[0][j], (RM)x[0]) : (RM)0;
 #pragma unroll
-                for (int h = 0; h < RPL; h++) if (l + h * G < n) v += Y[h][j] * (RM)x[h];
+                for (int h = 1; h < RPL; h++) if (l + h * G < n) v = coop_add_rn(v, coop_mul_rn(Y[h][j], (RM)x[h]));
                 zs[j] = group_sum<G>(v);
             });
         }
@@ -951,9 +967,10 @@ COOP_GLOBAL void k_substep_coop(const COOP_GRID_CONSTANT PModel<R> M, const Coop
     const int w = (blockIdx.x * nwarps + warp) * C::WPW + gi;
     const bool wactive = w < n;
     CoopRows<T, R>* rows = reinterpret_cast<CoopRows<T, R>*>(smraw) + (warp * C::WPW + gi);
+    const bool mine = wactive && l < NB;
     const CoopLane<T, R> c = tab[l];
-    const bool mine = wactive && c.isb;
-    R q = mine ? qs[(size_t)l * n + w] : c.qinit, dq = mine ? dqs[(size_t)l * n + w] : (R)0;
+    R q = mine ? qs[(size_t)l * n + w] : (R)0, dq = mine ? dqs[(size_t)l * n + w] : (R)0;
+    if (!mine) q = c.qinit;
     const R tau = (mine && tau_in) ? tau_in[(size_t)w * NB + l] : (R)0;
     uint32_t hint = 0xffffffffu;   // the literal World.step() drop-in is stateless
     coop_substep<T, R, false>(M, c, gbase, q, dq, tau, (R)0, (R)0, lcp_mode, pgs_iters, &sink, wactive, w, hint, rows);
@@ -974,14 +991,19 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     const bool wactive = w < a.n;
     CoopRows<T, R>* rows = reinterpret_cast<CoopRows<T, R>*>(smraw) + (warp * WPW + gi);
     float* sobs = reinterpret_cast<float*>(smraw + (size_t)nwarps * WPW * sizeof(CoopRows<T, R>)) + (size_t)warp * WPW * K.n_obs;
+    // every global load of the step is issued up front and none depends on another (one DRAM round trip)
+    const bool mine = wactive && l < NB;
     const CoopLane<T, R> c = tab[l];
-    const bool mine = wactive && c.isb;
+    R q = mine ? a.q[(size_t)l * a.n + w] : (R)0, dq = mine ? a.dq[(size_t)l * a.n + w] : (R)0;
+    const R araw = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
+    const int el_in = (wactive && l == 0 && a.max_episode_steps > 0) ? a.elapsed[w] : 0;
+    const uint32_t ep_in = (wactive && l == 0) ? a.episode[w] : 0u;
+    uint32_t hint = wactive ? (uint32_t)a.hint[w] : 0xffffffffu;
+    if (!mine) q = c.qinit;
     // this dof's actuator (hopper.py:24-32: clamp, scale, scatter)
     const int act = c.act, pen_dof = c.pen_dof;
     const R ascale = c.ascale, alo = c.alo, ahi = c.ahi;
-    R q = mine ? a.q[(size_t)l * a.n + w] : c.qinit, dq = mine ? a.dq[(size_t)l * a.n + w] : (R)0;
     // control cost uses the RAW action, summed in action order
-    const R araw = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
     R a2 = 0, tau = 0;
     static_for<0, G>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
@@ -991,7 +1013,6 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     });
     if (!mine) tau = 0;
     const R posbefore = gshfl<G>(q, 0);
-    uint32_t hint = wactive ? (uint32_t)a.hint[w] : 0xffffffffu;
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (f == K.frame_skip - 1 && (a.sink.count || a.sink.body || a.sink.data)) ? &a.sink : nullptr;
         coop_substep<T, R, FLUID>(M, c, gbase, q, dq, tau, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, wactive, w, hint, rows);
@@ -1031,8 +1052,8 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     bool done = !ok;
     bool trunc = false;
     // per-world counters: lane 0 of the group reads, everyone learns the value, lane 0 writes back
-    const int el = gshfl<G>((wactive && l == 0 && a.max_episode_steps > 0) ? a.elapsed[w] + 1 : 0, 0);
-    const uint32_t ep = gshfl<G>((wactive && l == 0) ? a.episode[w] : 0u, 0);
+    const int el = gshfl<G>(el_in + 1, 0);
+    const uint32_t ep = gshfl<G>(ep_in, 0);
     if (wactive && a.max_episode_steps > 0) {
         if (el >= a.max_episode_steps) { trunc = !done; done = true; }
         if (l == 0) a.elapsed[w] = (done && a.auto_reset) ? 0 : el;

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 def _cooperative_kernel():
     P.VARIANT = 2
     yield
-    P.VARIANT = None
+    P.VARIANT = 0
 
 
 @pytest.mark.parametrize("env_id", list(SPECS))
@@ -55,3 +55,22 @@ def test_closed_loop_equals_per_thread_kernel_fp64(models, env_id):
             assert np.allclose(q0.cpu().numpy()[m], q2.cpu().numpy()[m], rtol=1e-6, atol=1e-7)
             assert np.allclose(r0.cpu().numpy()[m], r2.cpu().numpy()[m], rtol=1e-4, atol=1e-4)
             assert np.allclose(o0.cpu().numpy()[m], o2.cpu().numpy()[m], rtol=1e-4, atol=1e-5)
+
+
+def test_automatic_kernel_choice_by_batch_size(models):
+    """Small batches run the cooperative form, large ones the per-thread form (dartb.cu::lower_into); either can
+    be forced.  Bit-exact shard == batch holds within one form; across forms trajectories agree to fp32 tolerance
+    and the reset noise (keyed by global world id) is identical."""
+    P.VARIANT = None
+    try:
+        for env_id, small, large in (("DartHopper-v1", 4096, 16384), ("DartHalfCheetah-v1", 4096, 16384), ("DartSnake7Link-v1", 1024, 4096)):
+            a = P._engine(models, env_id, small, seed=1)
+            b = P._engine(models, env_id, large, seed=1)
+            assert "coop:" in a.kernel_name and "static:" in b.kernel_name, (a.kernel_name, b.kernel_name)
+            a.reset(); b.reset()
+            qa, _ = a.get_state(torch.float64)
+            qb, _ = b.get_state(torch.float64)
+            assert torch.equal(qa, qb[:small])      # same reset draws whichever kernel runs
+            a.close(); b.close()
+    finally:
+        P.VARIANT = 2

@@ -29,7 +29,8 @@ ENVS = list(SPECS)
 MARGIN = 1e-4
 
 
-VARIANT = None   # tests/test_gpu_coop.py re-runs this module's tests with the lane-cooperative kernel (2)
+VARIANT = 0   # this module pins the one-world-per-thread kernels; tests/test_gpu_coop.py re-runs its tests with the
+              # lane-cooperative kernels (2).  (None = the engine's automatic choice by batch size.)
 
 
 def _engine(models, env_id, n, **kw):

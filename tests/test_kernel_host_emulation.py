@@ -18,6 +18,7 @@ FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
 
 
 VARIANTS = [0, 1]  # 0 = unrolled per-topology kernel, 1 = loop / topology-generic kernel
+# (2 = lane-cooperative kernel: its own tests below, under the SIMT emulator of tools/host_emu/simt.h)
 
 
 def _run(models, env_id, f64, **kw):
@@ -115,3 +116,74 @@ def test_kernel_lcp_solvers_equal_oracle_dantzig(mode, maxn):
         err = np.abs(A @ (x - xr)).max() / (1 + np.abs(A @ xr).max())
         worst = max(worst, err)
     assert worst < 1e-6, worst
+
+
+# ------------------------------------------------------------------ lane-cooperative kernel (planar_coop.cuh)
+def _run_coop(models, env_id, f64, idx=None, **kw):
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0   # the cooperative kernel takes no external forces
+    sel = np.where(nf)[0] if idx is None else np.asarray(idx)
+    out = emu.substep(models[env_id], SPECS[env_id].task, g["sub_q"][sel], g["sub_dq"][sel], g["sub_tau"][sel], None,
+                      f64=f64, maxc=8, variant=2, **kw)
+    return g, sel, out
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_cooperative_kernel_fp64_equals_oracle(models, env_id):
+    """G lanes per world (prefix-sum kinematics, CRBA + sparse LTL, distributed LCP) == the 3-D fp64 oracle."""
+    g, sel, (q2, dq2, cnt, body, data) = _run_coop(models, env_id, True)
+    safe = g["sub_contact_margin"][sel] > 1e-9    # exact-touch samples may flip: a different (but valid) summation order
+    assert safe.mean() > 0.95
+    assert np.allclose(q2[safe], g["sub_q2"][sel][safe], rtol=1e-9, atol=1e-10)
+    assert np.allclose(dq2[safe], g["sub_dq2"][sel][safe], rtol=1e-8, atol=1e-8)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])
+    tie_ok = safe & (g["sub_tie_margin"][sel] > 1e-9)
+    assert np.array_equal(body[tie_ok], g["sub_contact_body"][sel][tie_ok])
+    assert np.allclose(data[tie_ok][..., :7], g["sub_contact_data"][sel][tie_ok][..., :7], atol=1e-6)
+    assert np.allclose(data[tie_ok][..., 7:], g["sub_contact_data"][sel][tie_ok][..., 7:], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_cooperative_kernel_fp32_within_tolerance(models, env_id):
+    """fp32 engine with the fp64 mass-matrix core: TIGHTER than the per-thread fp32 kernel's stated tolerance."""
+    g, sel, (q2, dq2, cnt, body, data) = _run_coop(models, env_id, False)
+    safe = (g["sub_contact_margin"][sel] > 1e-4) & (g["sub_limit_margin"][sel] > 1e-4) & (g["sub_tie_margin"][sel] > 1e-4)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])
+    assert np.array_equal(body[safe], g["sub_contact_body"][sel][safe])
+    ev = (np.abs(dq2 - g["sub_dq2"][sel]) / (1 + np.abs(g["sub_dq2"][sel])))[safe].max(1)
+    eq = (np.abs(q2 - g["sub_q2"][sel]) / (1 + np.abs(g["sub_q2"][sel])))[safe].max(1)
+    assert np.median(ev) < 2e-6 and np.percentile(ev, 99) < 5e-4 and ev.max() < 5e-2 and eq.max() < 2e-4
+
+
+def test_cooperative_kernel_world_independent_of_warp_neighbours(models):
+    """A warp picks ONE LCP column class from its largest row count; a world's result must not depend on the
+    class its neighbours put it in (shard == batch, bit for bit)."""
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
+    rows = g["sub_lcp_rows"]
+    small = np.where(nf & (rows >= 1) & (rows <= 4))[0][:6]
+    big = np.where(nf & (rows >= 5))[0][:6]
+    assert len(small) == 6 and len(big) >= 2
+    for f64 in (True, False):
+        _, _, (qa, dqa, *_r) = _run_coop(models, env_id, f64, idx=small)                      # warps of small worlds only
+        mixed = np.array([v for pair in zip(small, np.resize(big, 6)) for v in pair])        # every warp holds a big one
+        _, _, (qm, dqm, *_r) = _run_coop(models, env_id, f64, idx=mixed)
+        assert np.array_equal(qa, qm[0::2]) and np.array_equal(dqa, dqm[0::2])
+
+
+def test_cooperative_kernel_pgs_equals_oracle_pgs(models):
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
+    idx = np.where(nf & (g["sub_ncontact"] > 0))[0][:30]
+    for iters in (1, 5, 30):
+        w = orc.OracleWorld(models[env_id])
+        w.set_option(1, 1); w.set_option(2, iters)
+        ref = []
+        for i in idx:
+            w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+            ref.append(np.concatenate(w.get_state()))
+        _, _, (q2, dq2, *_r) = _run_coop(models, env_id, True, idx=idx, lcp_mode=1, pgs_iters=iters)
+        assert np.allclose(np.concatenate([q2, dq2], 1), np.array(ref), rtol=1e-8, atol=1e-8)

@@ -27,7 +27,7 @@ e0.record()
 for i in range(K): eng.step(acts[i %% 16], env._obs, env._rew, env._done, True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print("%%-20s n=%%7d wpw=%%4s block=%%4s lcp=%%s %%8.1f us/step  %%.3e env-steps/s  [%%s]" %% (env_id, n, os.environ.get("DARTB_WPW", "auto"), os.environ.get("DARTB_BLOCK", "auto"), os.environ.get("SWEEP_PGS", "exact"), ms * 1e3, n / (ms * 1e-3), eng.kernel_name))
+print("%%-20s n=%%7d wpw=%%4s block=%%4s cw=%%s lcp=%%s %%8.1f us/step  %%.3e env-steps/s  [%%s]" %% (env_id, n, os.environ.get("DARTB_WPW", "auto"), os.environ.get("DARTB_BLOCK", "auto"), os.environ.get("DARTB_COOP_WARPS", "-"), os.environ.get("SWEEP_PGS", "exact"), ms * 1e3, n / (ms * 1e-3), eng.kernel_name))
 ''' % ROOT
 
 cfgs = []
@@ -45,6 +45,15 @@ elif mode == "main":
 elif mode == "coop":   # per-thread (0) vs lane-cooperative (2) kernels across batch sizes
     for env_id, sizes in (("DartHopper-v1", (1024, 4096, 16384, 65536)), ("DartWalker2d-v1", (4096, 16384)),
                           ("DartHalfCheetah-v1", (4096, 16384)), ("DartSnake7Link-v1", (4096, 32768))):
+        for n in sizes:
+            for v in ("0", "2"):
+                cfgs.append((env_id, n, "32" if n <= 4096 else "128", v))
+elif mode == "coopw":   # cooperative kernel: warps per block, and the crossover batch sizes
+    for cw in ("1", "2", "4"):
+        for env_id, n in (("DartHopper-v1", 4096), ("DartHalfCheetah-v1", 4096)):
+            cfgs.append((env_id, n, "32", "2", "", "", cw))
+    for env_id, sizes in (("DartHopper-v1", (2048, 6144, 8192, 12288)), ("DartWalker2d-v1", (2048, 8192)), ("DartHalfCheetah-v1", (2048, 8192, 12288)),
+                          ("DartSnake7Link-v1", (512, 1024, 2048))):
         for n in sizes:
             for v in ("0", "2"):
                 cfgs.append((env_id, n, "32" if n <= 4096 else "128", v))
@@ -70,7 +79,9 @@ for cfg in cfgs:
     env = dict(os.environ, DARTB_BLOCK=b, DARTB_VARIANT=v, DART_ENV_NO_REFERENCE="1")
     if len(cfg) > 4 and cfg[4]:
         env["SWEEP_PGS"] = cfg[4]
-    if len(cfg) > 5:
+    if len(cfg) > 5 and cfg[5]:
         env["DARTB_WPW"] = cfg[5]
+    if len(cfg) > 6:
+        env["DARTB_COOP_WARPS"] = cfg[6]
     r = subprocess.run([sys.executable, "-c", CODE, env_id, str(n)], env=env, capture_output=True, text=True)
     print("variant=%s " % v + (r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)

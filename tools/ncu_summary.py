@@ -11,6 +11,7 @@ import subprocess
 import sys
 
 rep, out, env_id = sys.argv[1], sys.argv[2], sys.argv[3]
+json_key = sys.argv[4] if len(sys.argv) > 4 else env_id   # e.g. "DartHopper-v1/static" keeps an older capture beside the current one
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -87,9 +88,23 @@ summary = {"kernel": L["kernel"][:80], "duration_us": L["gpu__time_duration.sum"
            "grid": L.get("launch__grid_size"), "block": L.get("launch__block_size"), "stall_pct": stalls,
            "fp32": {"flop_per_launch": flops, "achieved_tflops_under_ncu": flops / dur_s / 1e12 if dur_s else None,
                     "note": "FADD+FMUL+2*FFMA thread instructions; B200 non-tensor fp32 peak ~ 74 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz)"}}
+# fp64 work (the cooperative kernels carry the mass-matrix core in fp64): thread-level DFMA / DMUL / DADD from the SASS page
+sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+sr = list(csv.reader(io.StringIO(sass)))
+if len(sr) > 2:
+    h2 = {h: k for k, h in enumerate(sr[1])}
+    f64 = 0
+    for r in sr[2:]:
+        t = r[1].strip().split()
+        if not t:
+            continue
+        o = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+        if o in ("DFMA", "DMUL", "DADD"):
+            f64 += (2 if o == "DFMA" else 1) * int(r[h2["Predicated-On Thread Instructions Executed"]])
+    summary["fp64"] = {"flop_per_launch": f64, "note": "DADD+DMUL+2*DFMA thread instructions (fp64 mass-matrix core of the cooperative kernel)"}
 jpath = os.path.join(os.path.dirname(out), "r1_ncu_summary.json")
 allj = json.load(open(jpath)) if os.path.exists(jpath) else {}
-allj[env_id] = summary
+allj[json_key] = summary
 json.dump(allj, open(jpath, "w"), indent=1)
 with open(out + "_ncu_summary.md", "w") as fh:
     fh.write("# ncu summary: %s\n\nsource: `%s` (`ncu --set full --clock-control none --import-source on`), read with `ncu -i`.\n\n" % (env_id, os.path.basename(rep)))
