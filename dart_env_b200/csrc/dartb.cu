@@ -71,6 +71,7 @@ struct dartb_engine {
     int64_t launches = 0;
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
     float* h_stage = nullptr; float* d_stage = nullptr; float* h_stage_dev = nullptr; size_t stage_floats = 0;
+    const void* zc_h[3] = {nullptr, nullptr, nullptr}; void* zc_d[3] = {nullptr, nullptr, nullptr};   // zero-copy output aliases
     std::string kernel_name;
 };
 
@@ -484,9 +485,14 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
         // moving these ~250 KB does).  Pageable caller buffers go through the pinned staging block.
         const float* a_dev = (const float*)mapped_alias(h_action);
         if (!a_dev) { std::memcpy(e->h_stage, h_action, fa * 4); a_dev = e->h_stage_dev; }
-        float* o_dev = (float*)mapped_alias(h_obs);
-        float* r_dev = (float*)mapped_alias(h_reward);
-        uint8_t* d_dev = (uint8_t*)mapped_alias(h_done);
+        // (the caller's output buffers are normally the same page-locked arrays every step: look them up once)
+        if (h_obs != e->zc_h[0] || h_reward != e->zc_h[1] || h_done != e->zc_h[2]) {
+            e->zc_h[0] = h_obs; e->zc_h[1] = h_reward; e->zc_h[2] = h_done;
+            e->zc_d[0] = mapped_alias(h_obs); e->zc_d[1] = mapped_alias(h_reward); e->zc_d[2] = mapped_alias(h_done);
+        }
+        float* o_dev = (float*)e->zc_d[0];
+        float* r_dev = (float*)e->zc_d[1];
+        uint8_t* d_dev = (uint8_t*)e->zc_d[2];
         const bool direct = o_dev && r_dev && d_dev;
         if (!direct) { o_dev = e->h_stage_dev + fa; r_dev = o_dev + fo; d_dev = (uint8_t*)(r_dev + fr); }
         int rc = e->f64 ? launch_step<double>(e, a_dev, o_dev, r_dev, d_dev, auto_reset, st)

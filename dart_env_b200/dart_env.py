@@ -15,6 +15,7 @@ Return types
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import Optional, Sequence
 
@@ -125,6 +126,7 @@ class DartEnv:
         self._n_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory().numpy()
         self._n_rew = torch.empty((n,), dtype=torch.float32).pin_memory().numpy()
         self._n_done = torch.empty((n,), dtype=torch.uint8).pin_memory().numpy()
+        self._c_obs, self._c_rew, self._c_done = (C.c_void_p(x.ctypes.data) for x in (self._n_obs, self._n_rew, self._n_done))
 
     @property
     def max_episode_steps(self):
@@ -224,8 +226,16 @@ class DartEnv:
             self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)
         else:
             # host path: one library call does pinned H2D, the launch, one D2H and the sync
-            act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
-            self.engine.step_host(act, self._n_obs, self._n_rew, self._n_done, self.auto_reset)
+            act = a
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == (self.num_envs, self.act_dim)
+                    and a.flags.c_contiguous):
+                act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
+            # (the output arrays are this env's own page-locked buffers: their pointers are cached)
+            eng = self.engine
+            rc = eng.L.dartb_step_host(eng.h, act.ctypes.data, self._c_obs, self._c_rew, self._c_done, int(self.auto_reset),
+                                       eng._stream())
+            if rc:
+                capi.check(rc)
             d = self._n_done  # bit 0 done, bit 1 truncated by the time limit (no extra transfer)
             if self.batched:
                 infos = {}
