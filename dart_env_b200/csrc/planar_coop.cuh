@@ -167,15 +167,14 @@ DEVI void anc_prefix(const CoopLane<T, R>& c, R (&x)[K]) {
     }
 }
 
-// 1/sqrt(x) for the mass-matrix core.  FAST (the fp32 engine's fp64 core): MUFU.RSQ seed + two Newton
-// steps (rel. error ~1e-15) instead of the ~100-instruction IEEE sqrt + divide sequence; the fp64
-// validation engine keeps the exact one.
+// 1/sqrt(x) for the mass-matrix core.  FAST (the fp32 engine's fp64 core): MUFU.RSQ seed (2^-22) + one
+// Newton step (rel. error ~1e-13, far below the fp32 kinematics it serves) instead of the
+// ~100-instruction IEEE sqrt + divide sequence; the fp64 validation engine keeps the exact one.
 template <bool FAST, typename RM>
 DEVI RM mass_rsqrt(RM x) {
     if constexpr (FAST && std::is_same<RM, double>::value) {
         const double h = 0.5 * x;
         double y = (double)Num<float>::rsqrt_((float)x);
-        y = y * (1.5 - h * y * y);
         y = y * (1.5 - h * y * y);
         return y;
     } else return Num<RM>::rsqrt_(x);
@@ -199,6 +198,30 @@ DEVI void ltl_factor(R (&A)[T::NB][T::NB], R (&Li)[T::NB]) {
                 static_for<0, i + 1>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     if constexpr (C::anc(j, k)) A[i][j] -= A[k][i] * A[k][j];
+                });
+            }
+        });
+    });
+}
+// Two independent factorisations statement by statement, so the two dependent chains (rsqrt -> scale ->
+// update per column) interleave in the instruction stream of a warp that has nothing else to issue.
+template <class T, typename R, bool FAST = false>
+DEVI void ltl_factor2(R (&A)[T::NB][T::NB], R (&La)[T::NB], R (&B)[T::NB][T::NB], R (&Lb)[T::NB]) {
+    using C = Coop<T>;
+    static_rfor<T::NB>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        La[k] = mass_rsqrt<FAST, R>(A[k][k]);
+        Lb[k] = mass_rsqrt<FAST, R>(B[k][k]);
+        static_for<0, k>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (C::anc(i, k)) { A[k][i] *= La[k]; B[k][i] *= Lb[k]; }
+        });
+        static_for<0, k>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (C::anc(i, k)) {
+                static_for<0, i + 1>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    if constexpr (C::anc(j, k)) { A[i][j] -= A[k][i] * A[k][j]; B[i][j] -= B[k][i] * B[k][j]; }
                 });
             }
         });
@@ -847,6 +870,7 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
         });
     });
     // ---------------- K3: (M + dt D + dt^2 K) ddq = tau - c - K (q - rest + dt dq) - D dq
+    RM Lp[NB];   // 1 / diag of the factor of the plain M (filled here when NS > 0, else on demand below)
     {
         const R rhs = c.isb ? tau - cb - c.ksp * (q - c.rest + dt * dq) - c.damp * dq : (R)0;
         RM xg[NB], Mt[NB][NB], Li[NB];
@@ -859,7 +883,10 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
             });
             Mt[i][i] += (RM)dt * (RM)M.damping[i] + (RM)dt * (RM)dt * (RM)M.kspring[i];
         });
-        ltl_factor<T, RM, FASTM>(Mt, Li);
+        // skeletons with capsules nearly always have constraint rows somewhere in the warp: factor the plain M
+        // (needed for the impulse tests) together with the implicit one instead of after the collision phase
+        if constexpr (NS > 0) { ltl_factor2<T, RM, FASTM>(Mt, Li, Mf, Lp); }
+        else ltl_factor<T, RM, FASTM>(Mt, Li);
         ltl_solve_t<T, RM>(Mt, Li, xg);
         ltl_solve<T, RM>(Mt, Li, xg);
         RM ddq = 0;
@@ -913,16 +940,15 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
     if (nmax > 0) {
         // plain M = L^T L for the impulse tests (DART uses the non-implicit articulated inertia there)
         using RC = RM;
-        RC Li[NB];
-        ltl_factor<T, RC, FASTM>(Mf, Li);
+        if constexpr (NS == 0) ltl_factor<T, RC, FASTM>(Mf, Lp);
         CoopContact<R> ct;
         ct.hasc = hasc; ct.fric = fric; ct.Px = cPx; ct.Py = cPy; ct.nx = cnx; ct.ny = cny; ct.depth = cdepth; ct.mu = cmu;
         ct.lact = lact; ct.cm = cm; ct.fm = fm; ct.lm = lm; ct.Ox = Ox; ct.Oy = Oy;
         // the size class is chosen per warp, so a warp runs one code path
-        if (nmax <= 4 && C::NC >= 4) coop_constraints<T, R, RC, FLUID, 4>(M, c, gbase, dq, ct, n, nmax, Mf, Li, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
-        else if (nmax <= 8 && C::NC >= 8) coop_constraints<T, R, RC, FLUID, (C::NC >= 8 ? 8 : C::NC)>(M, c, gbase, dq, ct, n, nmax, Mf, Li, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
-        else if (nmax <= 16 && C::NC >= 16) coop_constraints<T, R, RC, FLUID, (C::NC >= 16 ? 16 : C::NC)>(M, c, gbase, dq, ct, n, nmax, Mf, Li, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
-        else coop_constraints<T, R, RC, FLUID, C::NC>(M, c, gbase, dq, ct, n, nmax, Mf, Li, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
+        if (nmax <= 4 && C::NC >= 4) coop_constraints<T, R, RC, FLUID, 4>(M, c, gbase, dq, ct, n, nmax, Mf, Lp, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
+        else if (nmax <= 8 && C::NC >= 8) coop_constraints<T, R, RC, FLUID, (C::NC >= 8 ? 8 : C::NC)>(M, c, gbase, dq, ct, n, nmax, Mf, Lp, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
+        else if (nmax <= 16 && C::NC >= 16) coop_constraints<T, R, RC, FLUID, (C::NC >= 16 ? 16 : C::NC)>(M, c, gbase, dq, ct, n, nmax, Mf, Lp, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
+        else coop_constraints<T, R, RC, FLUID, C::NC>(M, c, gbase, dq, ct, n, nmax, Mf, Lp, Pgx, Pgy, Ugx, Ugy, lcp_mode, pgs_iters, sink, world, hint, rows);
     } else {
         hint = 0xffffffffu;
     }
