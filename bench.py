@@ -276,10 +276,16 @@ def run_ours(args, rank, local_rank, world_size):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": eng.kernel_name,
                 "note": "fused per-world stepper: only the API-boundary I/O (%d B/env-step) crosses HBM, so the HBM "
-                        "fraction is small by construction; the kernel is fp32-issue/latency bound (see profiles/)"
+                        "fraction is small by construction; the kernel is bound by dependent-issue latency (see profiles/)"
                         % (bytes_per_launch // n)}
-        if isinstance(prof, dict) and args.env in prof and "fp32" in prof[args.env]:
-            roof["fp32"] = prof[args.env]["fp32"]
+        # counted arithmetic of the captured kernel form (profiles/): key "<env>" = lane-cooperative, "<env>/static" = per-thread
+        pkey = args.env if "coop:" in eng.kernel_name or (args.env + "/static") not in prof else args.env + "/static"
+        if isinstance(prof, dict) and pkey in prof:
+            roof["traffic"] = prof[pkey].get("dram_bytes_per_launch", traffic)
+            for k in ("fp32", "fp64"):
+                if k in prof[pkey]:
+                    roof[k] = prof[pkey][k]
+            roof["profile"] = "profiles/r1_ncu_summary.json[%s]" % pkey
         cb = None
         if world_size >= 1:
             cb, _, _ = cpu_arm(args.env, n, None, 5, host_threads(), budget_s=12.0)
