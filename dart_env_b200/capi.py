@@ -15,7 +15,7 @@ _EXPORTS = [
     "dartb_get_state", "dartb_set_state_f64", "dartb_get_state_f64", "dartb_step", "dartb_substep",
     "dartb_substep_f64", "dartb_get_contacts", "dartb_get_truncated", "dartb_max_contacts", "dartb_num_worlds",
     "dartb_num_dofs", "dartb_is_f64", "dartb_launch_count", "dartb_kernel_name", "dartb_last_error",
-    "dartb_version", "dartb_describe", "dartb_step_host",
+    "dartb_version", "dartb_describe", "dartb_step_host", "dartb_step_host_gym",
 ]
 
 
@@ -57,6 +57,7 @@ def load(build_if_missing: bool = True):
         "dartb_step": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
         "dartb_substep": (C.c_int, [vp, vp, vp, vp]),
         "dartb_step_host": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
+        "dartb_step_host_gym": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp]),
         "dartb_substep_f64": (C.c_int, [vp, vp, vp, vp]),
         "dartb_get_contacts": (C.c_int, [vp, vp, vp, vp, vp]),
         "dartb_get_truncated": (C.c_int, [vp, vp, vp]),

@@ -454,6 +454,21 @@ static void* mapped_alias(const void* h) {
     return nullptr;
 }
 
+// the pinned (host-mapped) staging block of the host-facing step and its device mirror
+static int ensure_stage(dartb_engine* e, size_t need) {
+    if (e->stage_floats >= need) return 0;
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->h_stage = nullptr; e->d_stage = nullptr; e->h_stage_dev = nullptr; e->stage_floats = 0;
+    CK(cudaHostAlloc((void**)&e->h_stage, need * 4, cudaHostAllocMapped));
+    CK(cudaMalloc((void**)&e->d_stage, need * 4));
+    void* alias = nullptr;
+    if (cudaHostGetDevicePointer(&alias, e->h_stage, 0) == cudaSuccess) e->h_stage_dev = (float*)alias;
+    cudaGetLastError();
+    e->stage_floats = need;
+    return 0;
+}
+
 int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done,
                     int32_t auto_reset, void* stream) {
     if (!e) return fail("null handle");
@@ -464,17 +479,7 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     // layout of the staging block (floats): [action n*na | obs n*no | reward n | done n bytes]
     const size_t fa = (size_t)n * na, fo = (size_t)n * no, fr = (size_t)n, fd = ((size_t)n + 3) / 4;
     const size_t need = fa + fo + fr + fd;
-    if (e->stage_floats < need) {
-        if (e->h_stage) cudaFreeHost(e->h_stage);
-        if (e->d_stage) cudaFree(e->d_stage);
-        e->h_stage = nullptr; e->d_stage = nullptr; e->h_stage_dev = nullptr; e->stage_floats = 0;
-        CK(cudaHostAlloc((void**)&e->h_stage, need * 4, cudaHostAllocMapped));
-        CK(cudaMalloc((void**)&e->d_stage, need * 4));
-        void* alias = nullptr;
-        if (cudaHostGetDevicePointer(&alias, e->h_stage, 0) == cudaSuccess) e->h_stage_dev = (float*)alias;
-        cudaGetLastError();
-        e->stage_floats = need;
-    }
+    if (ensure_stage(e, need)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     static int zc_env = -1;
     if (zc_env < 0) { const char* ev = getenv("DARTB_ZEROCOPY"); zc_env = ev ? atoi(ev) : 1; }
@@ -532,6 +537,31 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     return 0;
 }
 
+int dartb_step_host_gym(dartb_handle_t e, const float* h_action, float* obs_out, double* reward_out, uint8_t* done_out,
+                        uint8_t* truncated_out, int32_t auto_reset, void* stream) {
+    if (!e) return fail("null handle");
+    if (!h_action || !obs_out || !reward_out || !done_out) return fail("null host pointer");
+    if (e->task.n_obs == 0) return fail("physics-only handle: no task layer configured (use dartb_substep)");
+    const int n = e->n, na = e->task.n_act, no = e->task.n_obs;
+    const size_t fa = (size_t)n * na, fo = (size_t)n * no, fr = (size_t)n, fd = ((size_t)n + 3) / 4;
+    {
+        DeviceGuard g(e->device);
+        if (ensure_stage(e, fa + fo + fr + fd)) return 1;
+    }
+    // the kernel writes into the page-locked staging block (zero-copy); the conversion to the reference's
+    // return types (gym/vector/sync_vector_env.py:44-47: float64 rewards, bool dones) happens here, in one pass
+    float* so = e->h_stage + fa;
+    float* sr = so + fo;
+    uint8_t* sd = (uint8_t*)(sr + fr);
+    int rc = dartb_step_host(e, h_action, so, sr, sd, auto_reset, stream);
+    if (rc) return rc;
+    std::memcpy(obs_out, so, fo * 4);
+    for (int i = 0; i < n; i++) reward_out[i] = (double)sr[i];
+    for (int i = 0; i < n; i++) done_out[i] = sd[i] & 1;
+    if (truncated_out) for (int i = 0; i < n; i++) truncated_out[i] = (sd[i] >> 1) & 1;
+    return 0;
+}
+
 int dartb_substep(dartb_handle_t e, const float* d_tau, const float* d_fext, void* stream) {
     if (!e) return fail("null handle");
     DeviceGuard g(e->device);
@@ -585,6 +615,7 @@ int dartb_describe(const dartb_model_t* model, const dartb_task_t* task, char* b
     if (!model || !task || !buf || len < 2) return fail("null argument");
     dartb_engine e;
     e.model = *model; e.task = *task;
+    e.n = 1 << 30;   // describe the topology-level lowering (the batch-size dependent choice of the cooperative form is per handle)
     if (lower_into(&e)) return 1;
     std::snprintf(buf, (size_t)len, "%s nd=%d max_contacts=%d", e.kernel_name.c_str(), e.nd, e.max_contacts);
     return 0;

@@ -230,8 +230,21 @@ class DartEnv:
             if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == (self.num_envs, self.act_dim)
                     and a.flags.c_contiguous):
                 act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
-            # (the output arrays are this env's own page-locked buffers: their pointers are cached)
             eng = self.engine
+            if self.batched and self.copy:
+                # reference return types in one library call: fresh float32 obs, float64 rewards, bool dones
+                n = self.num_envs
+                obs = np.empty((n, self.obs_dim), dtype=np.float32)
+                rew = np.empty((n,), dtype=np.float64)
+                done = np.empty((n,), dtype=np.bool_)
+                trunc = np.empty((n,), dtype=np.bool_) if self._max_episode_steps else None
+                rc = eng.L.dartb_step_host_gym(eng.h, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                               trunc.ctypes.data if trunc is not None else None, int(self.auto_reset),
+                                               eng._stream())
+                if rc:
+                    capi.check(rc)
+                return obs, rew, done, ({"TimeLimit.truncated": trunc} if trunc is not None else {})
+            # (the output arrays are this env's own page-locked buffers: their pointers are cached)
             rc = eng.L.dartb_step_host(eng.h, act.ctypes.data, self._c_obs, self._c_rew, self._c_done, int(self.auto_reset),
                                        eng._stream())
             if rc:
@@ -241,8 +254,7 @@ class DartEnv:
                 infos = {}
                 if self._max_episode_steps:
                     infos["TimeLimit.truncated"] = (d & 2) != 0
-                obs = self._n_obs.copy() if self.copy else self._n_obs  # gym VectorEnv(copy=...) semantics
-                return obs, self._n_rew.astype(np.float64), d != 0, infos
+                return self._n_obs, self._n_rew.astype(np.float64), d != 0, infos
             info = {}
             done = bool(d[0] != 0)
             if self._max_episode_steps and done:

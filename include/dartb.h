@@ -149,6 +149,14 @@ int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_r
 int dartb_step_host(dartb_handle_t h, const float* h_action, float* h_obs, float* h_reward,
                     uint8_t* h_done, int32_t auto_reset, void* stream);
 
+/* The same step with the reference's vectorised RETURN TYPES (gym/vector/sync_vector_env.py:44-47,73-84):
+ * obs_out float32 [n, n_obs] (a fresh copy: VectorEnv(copy=True)), reward_out float64 [n], done_out bool [n]
+ * (1 byte each), truncated_out bool [n] or NULL (TimeLimit.truncated, gym/wrappers/time_limit.py:14-21).
+ * Any host memory (pageable is fine): the kernel writes into the engine's page-locked staging block and
+ * the conversion happens in one pass after the sync. */
+int dartb_step_host_gym(dartb_handle_t h, const float* h_action, float* obs_out, double* reward_out,
+                        uint8_t* done_out, uint8_t* truncated_out, int32_t auto_reset, void* stream);
+
 /* Exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175): one DART time step
  * with generalized forces d_tau [n, nd]; optional external world-frame forces at body
  * origins d_fext [n, n_bodies, 3] (bn.add_ext_force, snake_7link.py:47), may be NULL. */
