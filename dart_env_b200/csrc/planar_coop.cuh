@@ -322,10 +322,9 @@ struct CoopLcp {
 
     // Solve.  Per row slot h: A row, b, lo, hi (mu in hi for friction rows), fi (normal row of a friction
     // row, else -1), valid.  hin: hinted set of a friction row (3 = none).  Out: x, st.
-    static DEVI bool solve(const CoopLane<T, R>& c, int gbase, int n, int nmax, const R (&A)[RPL][NC], const R (&b)[RPL],
+    static DEVI bool solve(int l, int gbase, int n, int nmax, const R (&A)[RPL][NC], const R (&b)[RPL],
                            R (&lo)[RPL], R (&hi)[RPL], const int (&fi)[RPL], const unsigned (&hin)[RPL], R (&x)[RPL],
                            unsigned (&st)[RPL]) {
-        const int l = c.l;
         const R INF = Num<R>::inf();
         R Tb[RPL][NC], sd[RPL], mu[RPL];
         unsigned cur[RPL];
@@ -486,7 +485,7 @@ struct CoopLcp {
 
 // fixed-sweep projected Gauss-Seidel, rows on lanes (lcp_pgs of planar_kernels.cuh; DART PGSLCPSolver shape)
 template <class T, typename R, int NCx>
-DEVI void coop_pgs(const CoopLane<T, R>& c, int n, int nmax, const R (&A)[(NCx + Coop<T>::G - 1) / Coop<T>::G][NCx],
+DEVI void coop_pgs(int l, int n, int nmax, const R (&A)[(NCx + Coop<T>::G - 1) / Coop<T>::G][NCx],
                    const R (&b)[(NCx + Coop<T>::G - 1) / Coop<T>::G], const R (&lo)[(NCx + Coop<T>::G - 1) / Coop<T>::G],
                    const R (&hi)[(NCx + Coop<T>::G - 1) / Coop<T>::G], const int (&fi)[(NCx + Coop<T>::G - 1) / Coop<T>::G], int iters,
                    R (&x)[(NCx + Coop<T>::G - 1) / Coop<T>::G]) {
@@ -503,7 +502,7 @@ DEVI void coop_pgs(const CoopLane<T, R>& c, int n, int nmax, const R (&A)[(NCx +
             constexpr int dummy = 0; (void)dummy;
             const int h = i / G;
             R xi = 0;
-            if (c.l == i % G && i < n) {
+            if (l == i % G && i < n) {
                 R aii = 0, s = 0;
 #pragma unroll
                 for (int hh = 0; hh < RPL; hh++) if (hh == h) {
@@ -533,7 +532,7 @@ DEVI void coop_pgs(const CoopLane<T, R>& c, int n, int nmax, const R (&A)[(NCx +
     for (int h = 0; h < RPL; h++) {
         x[h] = 0;
 #pragma unroll
-        for (int cc = 0; cc < NC; cc++) { if (cc == c.l + h * G) x[h] = xa[cc]; }
+        for (int cc = 0; cc < NC; cc++) { if (cc == l + h * G) x[h] = xa[cc]; }
     }
 }
 
@@ -608,8 +607,13 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         __syncwarp();
         R dqg[NB];
         static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; dqg[i] = gshfl<G>(dq, i); });
+        // Rows 13+ only occur with six or more capsules on the ground at once (a fallen walker / cheetah): A is
+        // then rank-deficient up to the CFM and the fp32 tableau loses ~1e-4, so the two large column classes
+        // (never reached by the in-scope tasks' normal operation) run the LCP in the mass-matrix precision.
+        using RL = typename std::conditional<(NCx >= 16), RM, R>::type;
+        const RL INFL = Num<RL>::inf();
         RM Y[RPL][NB];
-        R bb[RPL], lo[RPL], hi[RPL];
+        RL bb[RPL], lo[RPL], hi[RPL];
         int fi[RPL], kind[RPL], rsrc[RPL];
         unsigned hin[RPL];
 #pragma unroll
@@ -634,10 +638,10 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
                     Y[h][j] = Jv;
                     vn += Jv * dqg[j];
                 });
-                bb[h] = bias - vn;
-                if (kind[h] == 1 || kind[h] == 3) { lo[h] = 0; hi[h] = INF; }
-                else if (kind[h] == 4) { lo[h] = -INF; hi[h] = 0; }
-                else { lo[h] = -mu; hi[h] = mu; fi[h] = r - 1; hin[h] = (hint >> (2 * rsrc[h])) & 3u; }
+                bb[h] = (RL)(bias - vn);
+                if (kind[h] == 1 || kind[h] == 3) { lo[h] = 0; hi[h] = INFL; }
+                else if (kind[h] == 4) { lo[h] = -INFL; hi[h] = 0; }
+                else { lo[h] = -(RL)mu; hi[h] = (RL)mu; fi[h] = r - 1; hin[h] = (hint >> (2 * rsrc[h])) & 3u; }
             }
             ltl_solve_t<T, RM>(Mf, Li, Y[h]);     // Y_r = L^-T J_r^T
         }
@@ -645,7 +649,7 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         // needs the impulses only (NC shuffles) instead of a NB-vector reduction over the group.
         constexpr bool KEEPY = NCx <= 4;
         RM Yall[KEEPY ? NC : 1][NB];
-        R A[RPL][NC];
+        RL A[RPL][NC];
 #pragma unroll
         for (int s = 0; s < NC; s++) {
             RM Ys[NB];
@@ -656,30 +660,30 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
                 RM v = 0;
                 static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; v += Y[h][j] * Ys[j]; });
                 if (s == l + h * G) v *= (RM)1 + (kind[h] <= 2 ? (RM)DK_CONTACT_CFM : (RM)DK_LIMIT_CFM);
-                A[h][s] = (R)v;
+                A[h][s] = (RL)v;
             }
         }
         // ---------------- K6
-        R x[RPL];
+        RL x[RPL];
         unsigned st[RPL];
         if (lcp_mode == 1) {
-            coop_pgs<T, R, NCx>(c, n, nmax, A, bb, lo, hi, fi, pgs_iters, x);
+            coop_pgs<T, RL, NCx>(l, n, nmax, A, bb, lo, hi, fi, pgs_iters, x);
 #pragma unroll
             for (int h = 0; h < RPL; h++) st[h] = 3u;
         } else {
-            const bool ok = CoopLcp<T, R, NCx>::solve(c, gbase, n, nmax, A, bb, lo, hi, fi, hin, x, st);
+            const bool ok = CoopLcp<T, RL, NCx>::solve(l, gbase, n, nmax, A, bb, lo, hi, fi, hin, x, st);
             // not converged (never observed): many PGS sweeps rather than leaving the rows unsolved
             const bool anybad = __any_sync(COOP_FULL, !ok);
             if (anybad) {
-                R x2[RPL], lo2[RPL], hi2[RPL];
+                RL x2[RPL], lo2[RPL], hi2[RPL];
 #pragma unroll
                 for (int h = 0; h < RPL; h++) {
                     // PGS bounds of a friction row are mu * x_normal: restore mu (solve() overwrote hi with |mu x_n|)
                     R mu = 0;
                     if (kind[h] == 2) { R w0, w1, w2, bias; RowIO<R>::get(rows, l + h * G, w0, w1, w2, bias, mu); }
-                    lo2[h] = kind[h] == 2 ? -mu : lo[h]; hi2[h] = kind[h] == 2 ? mu : hi[h];
+                    lo2[h] = kind[h] == 2 ? -(RL)mu : lo[h]; hi2[h] = kind[h] == 2 ? (RL)mu : hi[h];
                 }
-                coop_pgs<T, R, NCx>(c, n, nmax, A, bb, lo2, hi2, fi, 200, x2);
+                coop_pgs<T, RL, NCx>(l, n, nmax, A, bb, lo2, hi2, fi, 200, x2);
 #pragma unroll
                 for (int h = 0; h < RPL; h++) if (!ok) { x[h] = x2[h]; st[h] = 3u; }
             }
@@ -687,8 +691,8 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         // ---------------- K7: dq += L^-1 sum_r Y_r x_r
         RM zs[NB];
         if constexpr (KEEPY) {
-            R xs_[NC];
-            CoopLcp<T, R, NCx>::gather_rows(x, xs_, nmax);
+            RL xs_[NC];
+            CoopLcp<T, RL, NCx>::gather_rows(x, xs_, nmax);
             // summed in the order of the group_sum butterfly of the larger classes (products rounded one by
             // one, pairs (0,2) and (1,3) first), so a world's result does not depend on which class its warp
             // neighbours put it in

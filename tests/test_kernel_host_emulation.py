@@ -187,3 +187,35 @@ def test_cooperative_kernel_pgs_equals_oracle_pgs(models):
             ref.append(np.concatenate(w.get_state()))
         _, _, (q2, dq2, *_r) = _run_coop(models, env_id, True, idx=idx, lcp_mode=1, pgs_iters=iters)
         assert np.allclose(np.concatenate([q2, dq2], 1), np.array(ref), rtol=1e-8, atol=1e-8)
+
+
+def test_many_contact_states_large_column_classes(models):
+    """A fallen walker (13-16 LCP rows: six capsules on the ground + limits) drives the 16-column class of the
+    cooperative LCP and the thread-local pivoting of the per-thread kernel.  States are harvested from oracle
+    rollouts started in random tumbled poses; samples where the oracle's own Dantzig gave up are excluded."""
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    m, task = models[env_id], SPECS[env_id].task
+    rng = np.random.default_rng(1)
+    S = []
+    for trial in range(8):
+        w = orc.OracleWorld(m)
+        q = np.array(m.q_init(), dtype=float); dq = np.zeros_like(q)
+        q[2] = rng.uniform(-2.0, 2.0); q[1] += rng.uniform(-0.3, 0.1); q[3:] += rng.uniform(-0.6, 0.6, size=len(q) - 3)
+        w.set_state(q, dq)
+        for t in range(300):
+            tau = np.zeros(len(q)); tau[3:] = rng.uniform(-1, 1, size=len(q) - 3) * 30
+            s = w.get_state()
+            w.set_forces(tau); w.step()
+            n = 2 * len(w.contacts()) + int((w.limit_active() != 0).sum())
+            if n >= 13 and not w.lcp_failed() and t % 3 == 0:
+                S.append((s[0].copy(), s[1].copy(), tau.copy(), w.get_state()[1].copy()))
+    assert len(S) >= 10
+    q, dq, tau, ref = (np.array([s[k] for s in S]) for k in range(4))
+    for variant in (0, 2):
+        _, dq2, *_r = emu.substep(m, task, q, dq, tau, None, f64=True, maxc=8, variant=variant)
+        assert np.allclose(dq2, ref, rtol=1e-7, atol=1e-7), variant
+        _, dq2, *_r = emu.substep(m, task, q, dq, tau, None, f64=False, maxc=8, variant=variant)
+        ev = (np.abs(dq2 - ref) / (1 + np.abs(ref))).max(1)
+        # (fp32: A is rank-deficient up to the CFM here, cond ~ 1e5; the cooperative kernel runs these classes in fp64)
+        assert np.median(ev) < (2e-5 if variant == 2 else 1e-3) and ev.max() < 0.2, (variant, np.median(ev), ev.max())
