@@ -282,7 +282,7 @@ def run_ours(args, rank, local_rank, world_size):
         pkey = args.env if "coop:" in eng.kernel_name or (args.env + "/static") not in prof else args.env + "/static"
         if isinstance(prof, dict) and pkey in prof:
             roof["traffic"] = prof[pkey].get("dram_bytes_per_launch", traffic)
-            for k in ("fp32", "fp64"):
+            for k in ("fp32", "fp64", "issue_active_pct", "warps_active_pct", "stall_pct"):
                 if k in prof[pkey]:
                     roof[k] = prof[pkey][k]
             roof["profile"] = "profiles/r1_ncu_summary.json[%s]" % pkey

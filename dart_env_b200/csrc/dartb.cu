@@ -309,6 +309,8 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
     A((void**)&e->cdata, 4 * (size_t)n * e->max_contacts * 10);
     if (err != cudaSuccess) { dartb_destroy(e); return fail(std::string("cudaMalloc: ") + cudaGetErrorString(err)); }
     *out = e;
+    // the cooperative kernels' lane table is uploaded now, so that no launch ever synchronises
+    if (e->variant == 2 && (f64 ? coop_table_sync<double>(e, 0) : coop_table_sync<float>(e, 0))) { dartb_destroy(e); *out = nullptr; return 1; }
     // initial state = q_init / dq_init (the pydart World constructor resets the world)
     {
         const int nd = e->nd;
@@ -377,6 +379,14 @@ int dartb_destroy(dartb_handle_t e) {
     return 0;
 }
 
+// options that change the lowered model: lower again and refresh the lane table (the only synchronising path)
+static int relower(dartb_engine* e) {
+    if (lower_into(e)) return 1;
+    if (e->variant != 2) return 0;
+    DeviceGuard g(e->device);
+    return e->f64 ? coop_table_sync<double>(e, 0) : coop_table_sync<float>(e, 0);
+}
+
 int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
     if (!e) return fail("null handle");
     switch (key) {
@@ -388,11 +398,11 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             e->pgs_iters = (int)value; return 0;
         case DARTB_OPT_FRICTION_ALL:
             for (int i = 0; i < e->model.n_bodies; i++) e->model.bodies[i].friction_coeff = value;
-            return lower_into(e);
+            return relower(e);
         case DARTB_OPT_KERNEL_VARIANT:
             if (value != 0 && value != 1 && value != 2 && value != -1) return fail("kernel variant must be -1 (auto), 0 (unrolled), 1 (loop) or 2 (lane-cooperative)");
             e->variant_request = (int)value;
-            return lower_into(e);
+            return relower(e);
         case DARTB_OPT_WORLDS_PER_WARP:
             if (value < 0 || value > 32) return fail("worlds per warp must be 0 (auto) or 1..32");
             e->wpw_request = (int)value; return 0;

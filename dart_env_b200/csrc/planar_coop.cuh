@@ -974,7 +974,10 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
 #define COOP_GRID_CONSTANT
 #define COOP_SHARED_BYTES(name) unsigned char* name = (unsigned char*)simt::shared_ptr()
 #else
-#define COOP_GLOBAL __global__ __launch_bounds__(128)
+#ifndef DARTB_COOP_MIN_BLOCKS
+#define DARTB_COOP_MIN_BLOCKS 1
+#endif
+#define COOP_GLOBAL __global__ __launch_bounds__(128, DARTB_COOP_MIN_BLOCKS)
 #define COOP_GRID_CONSTANT __grid_constant__
 #define COOP_SHARED_BYTES(name) extern __shared__ __align__(16) unsigned char name[]
 #endif

@@ -193,15 +193,18 @@ def test_reset_noise_bit_exact_and_sharding_independent(models, env_id):
     eng.close(); eng2.close()
 
 
-def test_pgs_mode_matches_oracle_pgs(models):
-    """contact-rich PGS path (BASELINE config 3): same sweep count -> same iterate."""
+@pytest.mark.parametrize("env_id,sweep", [("DartWalker2d-v1", (1, 4, 30)), ("DartSnake7Link-v1", (1, 2, 4, 8, 16, 30, 50))])
+def test_pgs_mode_matches_oracle_pgs(models, env_id, sweep):
+    """contact-rich PGS path (BASELINE config 3) and the Snake PGS iteration sweep (config 5: its rows are
+    joint-limit rows only): same sweep count -> same iterate as the oracle's PGS."""
     from oracle import oracle as orc
-    env_id = "DartWalker2d-v1"
     g = _gold(env_id)
-    idx = np.where((g["sub_ncontact"] > 0) & (g["sub_contact_margin"] > MARGIN) & (g["sub_tie_margin"] > MARGIN)
+    has_rows = (g["sub_ncontact"] > 0) if env_id != "DartSnake7Link-v1" else (np.abs(g["sub_limit_active"]).sum(1) > 0)
+    idx = np.where(_no_fext(g) & has_rows & (g["sub_contact_margin"] > MARGIN) & (g["sub_tie_margin"] > MARGIN)
                    & (g["sub_limit_margin"] > MARGIN))[0][:40]
+    assert len(idx) >= 8
     dev = torch.device("cuda", 0)
-    for iters in (1, 4, 30):
+    for iters in sweep:
         ref = []
         w = orc.OracleWorld(models[env_id])
         w.set_option(1, 1); w.set_option(2, iters)
@@ -215,7 +218,7 @@ def test_pgs_mode_matches_oracle_pgs(models):
         eng.substep(torch.tensor(g["sub_tau"][idx], device=dev))
         q2, dq2 = eng.get_state(torch.float64)
         got = torch.cat([q2, dq2], 1).cpu().numpy()
-        assert np.allclose(got, ref, rtol=1e-8, atol=1e-8)
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-8), iters
         eng.close()
 
 

@@ -61,6 +61,10 @@ elif mode == "coopq":   # quick check of the cooperative kernel after a change
     for env_id, n in (("DartHopper-v1", 1024), ("DartHopper-v1", 4096), ("DartWalker2d-v1", 4096), ("DartHalfCheetah-v1", 4096),
                       ("DartSnake7Link-v1", 2048)):
         cfgs.append((env_id, n, "32", "2"))
+elif mode == "coopbig":   # cooperative kernel at large batches (register-cap experiments)
+    for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 16384), ("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384),
+                      ("DartHalfCheetah-v1", 4096)):
+        cfgs.append((env_id, n, "32" if n <= 4096 else "128", "2"))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):

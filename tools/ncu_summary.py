@@ -85,7 +85,9 @@ summary = {"kernel": L["kernel"][:80], "duration_us": L["gpu__time_duration.sum"
            "dram_bytes_per_launch": L.get("dram__bytes_read.sum", 0) + L.get("dram__bytes_write.sum", 0),
            "warp_inst_per_launch": L.get("smsp__inst_executed.sum"), "avg_active_lanes": L.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
            "ipc_per_sm": L.get("sm__inst_executed.avg.per_cycle_elapsed"), "registers": L.get("launch__registers_per_thread"),
-           "grid": L.get("launch__grid_size"), "block": L.get("launch__block_size"), "stall_pct": stalls,
+           "grid": L.get("launch__grid_size"), "block": L.get("launch__block_size"),
+           "issue_active_pct": L.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "warps_active_pct": L.get("sm__warps_active.avg.pct_of_peak_sustained_active"), "stall_pct": stalls,
            "fp32": {"flop_per_launch": flops, "achieved_tflops_under_ncu": flops / dur_s / 1e12 if dur_s else None,
                     "note": "FADD+FMUL+2*FFMA thread instructions; B200 non-tensor fp32 peak ~ 74 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz)"}}
 # fp64 work (the cooperative kernels carry the mass-matrix core in fp64): thread-level DFMA / DMUL / DADD from the SASS page
