@@ -65,6 +65,10 @@ elif mode == "coopbig":   # cooperative kernel at large batches (register-cap ex
     for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 16384), ("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384),
                       ("DartHalfCheetah-v1", 4096)):
         cfgs.append((env_id, n, "32" if n <= 4096 else "128", "2"))
+elif mode == "big":   # per-thread kernels at their large-batch sizes
+    for env_id, n in (("DartHopper-v1", 65536), ("DartHopper-v1", 16384), ("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384),
+                      ("DartSnake7Link-v1", 32768)):
+        cfgs.append((env_id, n, "128", "0"))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):
