@@ -516,166 +516,6 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     return true;
 }
 
-// ------------------------------------------------------------------------ K6 fast path, split stages
-// lcp_small with the rows PERMUTED so that the non-friction rows (normals, limits) lead: stage 1 (the
-// frictionless problem whose only purpose is to fix the friction bounds) then lives in the leading n1 x n1
-// block and runs the pivoting iteration at half the register size (NM/2: an eighth of the Cholesky work)
-// whenever every world of the warp has n1 <= NM/2; stage 2 runs at NM as before, from stage 1's sets.
-// One pivoting stage on the leading NA x NA block (rows >= NA are inactive: set 3, x = 0).
-// Returns 1 converged, 0 not converged, -1 not positive definite.
-template <typename R, int NM, int NA>
-DEVI int bpp_stage(const R (&A)[NM][NM], const R (&b)[NM], const R (&lo)[NM], const R (&hi)[NM], const R (&sd)[NM],
-                   R (&x)[NM], unsigned& st) {
-    int best = NA + 1, tries = 3;
-#pragma unroll 1
-    for (int it = 0; it < 6 + 3 * NA; it++) {
-        R L[NA][NA], y[NA];
-#pragma unroll
-        for (int i = 0; i < NA; i++) {
-            const unsigned si = (st >> (2 * i)) & 3u;
-            const R xb = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
-            if (si != 0) x[i] = xb;
-        }
-#pragma unroll
-        for (int i = 0; i < NA; i++) {
-            const bool fr = ((st >> (2 * i)) & 3u) == 0;
-            R r = b[i];
-#pragma unroll
-            for (int j = 0; j < NA; j++) {
-                const bool fj = ((st >> (2 * j)) & 3u) == 0;
-                if (!fj) r -= A[i][j] * x[j];
-            }
-            y[i] = fr ? r : (R)0;
-        }
-        bool pd = true;
-#pragma unroll
-        for (int i = 0; i < NA; i++) {
-            const bool fr = ((st >> (2 * i)) & 3u) == 0;
-#pragma unroll
-            for (int j = 0; j <= i; j++) {
-                const bool fj = ((st >> (2 * j)) & 3u) == 0;
-                R s = (fr && fj) ? A[i][j] : (i == j ? (R)1 : (R)0);
-#pragma unroll
-                for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-                if (i == j) { if (!(s > 0)) { pd = false; s = 1; } L[i][i] = Num<R>::rsqrt_(s); }
-                else L[i][j] = s * L[j][j];
-            }
-        }
-        if (!pd) return -1;
-#pragma unroll
-        for (int i = 0; i < NA; i++) {
-            R s = y[i];
-#pragma unroll
-            for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
-            y[i] = s * L[i][i];
-        }
-#pragma unroll
-        for (int i = NA - 1; i >= 0; i--) {
-            R s = y[i];
-#pragma unroll
-            for (int k = i + 1; k < NA; k++) s -= L[k][i] * y[k];
-            y[i] = s * L[i][i];
-        }
-#pragma unroll
-        for (int i = 0; i < NA; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
-        unsigned bad = 0, nst = st;
-        int nbad = 0;
-        R xs = 0, S = 0;
-#pragma unroll
-        for (int i = 0; i < NA; i++) { const R ax = Num<R>::abs_(x[i]); xs = ax > xs ? ax : xs; S += sd[i] * ax; }
-        const R tx = Num<R>::lcp_tol() * xs;
-#pragma unroll
-        for (int i = 0; i < NA; i++) {
-            const unsigned si = (st >> (2 * i)) & 3u;
-            if (si == 3) continue;
-            if (si == 0) {
-                if (x[i] < lo[i] - tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
-                else if (x[i] > hi[i] + tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
-            } else {
-                R w = -b[i];
-#pragma unroll
-                for (int j = 0; j < NA; j++) w += A[i][j] * x[j];
-                const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
-                if ((si == 1 && w < -tw) || (si == 2 && w > tw)) {
-                    if (lo[i] < hi[i]) { bad |= 1u << i; nbad++; nst = nst & ~(3u << (2 * i)); }
-                }
-            }
-        }
-        EMU_COUNT(4, 1);
-        if (nbad == 0) return 1;
-        if (nbad < best) { best = nbad; tries = 3; st = nst; }
-        else if (tries > 0) { tries--; st = nst; }
-        else {  // Murty: flip only the highest-index infeasible row (finite for P-matrices)
-            const int k = 31 - __clz(bad);
-            st = (st & ~(3u << (2 * k))) | (nst & (3u << (2 * k)));
-        }
-    }
-    return 0;
-}
-
-template <typename R, int NM>
-DEVI bool lcp_small2(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg,
-                     const uint8_t* hin = nullptr, uint8_t* sout = nullptr) {
-    // permutation: non-friction rows first (thread-local index arrays; the data already lives in local memory)
-    int perm[NM], inv[NM];
-    int n1 = 0;
-    for (int i = 0; i < n; i++) if (fidxg[i] < 0) { perm[n1] = i; inv[i] = n1; n1++; }
-    { int k = n1; for (int i = 0; i < n; i++) if (fidxg[i] >= 0) { perm[k] = i; inv[i] = k; k++; } }
-    for (int i = n; i < NM; i++) { perm[i] = 0; inv[i] = 0; }
-    R A[NM][NM], b[NM], lo[NM], hi[NM], x[NM], mu[NM], sd[NM];
-    int fi[NM];
-    unsigned hh[NM];
-    unsigned st = 0;  // 2 bits per row: 0 free, 1 at lo, 2 at hi, 3 permanently bound at x = 0
-    const R INF = Num<R>::inf();
-#pragma unroll
-    for (int i = 0; i < NM; i++) {
-        const bool on = i < n;
-        const int pi = perm[i];
-        b[i] = on ? bg[pi] : (R)0; lo[i] = on ? log_[pi] : (R)0; hi[i] = on ? hig[pi] : (R)0;
-        const int f = on ? fidxg[pi] : -1;
-        fi[i] = f >= 0 ? inv[f] : -1;
-        hh[i] = (hin && on) ? hin[pi] : 3u;
-        mu[i] = hi[i];
-        x[i] = 0;
-#pragma unroll
-        for (int j = 0; j < NM; j++) A[i][j] = (on && j < n) ? Ag[pi * n + perm[j]] : (i == j ? (R)1 : (R)0);
-        sd[i] = Num<R>::sqrt_(A[i][i]);
-        unsigned s = 0;
-        if (!on || !(A[i][i] > Num<R>::inert())) s = 3;           // padding / inert row
-        else if (fi[i] >= 0) s = 3;                                 // friction rows wait for stage 2
-        else if (lo[i] == 0 && hi[i] == INF) s = b[i] > 0 ? 0u : 1u;
-        else if (hi[i] == 0 && lo[i] == -INF) s = b[i] < 0 ? 0u : 2u;
-        st |= s << (2 * i);
-    }
-    // ---- stage 1: frictionless problem on the leading block
-    constexpr int NH = NM / 2;
-    const bool half = warp_max_active(n1) <= NH;
-    int rc = half ? bpp_stage<R, NM, NH>(A, b, lo, hi, sd, x, st) : bpp_stage<R, NM, NM>(A, b, lo, hi, sd, x, st);
-    if (rc <= 0) { EMU_COUNT(6, 1); return false; }
-    // ---- stage 2: friction bounds +-mu * x_n fixed from stage 1, hinted stick / slide sets
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < NM; i++) {
-        if (fi[i] >= 0 && i < n && A[i][i] > Num<R>::inert()) {
-            R xn = 0;
-#pragma unroll
-            for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
-            const R h = Num<R>::abs_(mu[i] * xn);
-            hi[i] = h; lo[i] = -h;
-            st &= ~(3u << (2 * i));
-            if (h == 0) st |= 3u << (2 * i);
-            else { any = true; if (hh[i] < 3u) st |= hh[i] << (2 * i); }   // hinted set, else free (sticking)
-        }
-    }
-    if (any) {
-        rc = bpp_stage<R, NM, NM>(A, b, lo, hi, sd, x, st);
-        if (rc <= 0) { EMU_COUNT(6, 1); return false; }
-    }
-#pragma unroll
-    for (int i = 0; i < NM; i++) if (i < n) { xg[perm[i]] = x[i]; if (sout) sout[perm[i]] = (uint8_t)((st >> (2 * i)) & 3u); }
-    return true;
-}
-
 // ------------------------------------------------------------------------ K6 fast path, tableau form
 // The same block-principal-pivoting iteration as lcp_small (same sets visited, same rounding-aware
 // tests), with the linear algebra kept as a PRINCIPAL PIVOT TRANSFORM of A instead of a fresh masked
@@ -970,10 +810,11 @@ DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int
     // Measured on B200 (gpurun A/B, 4096 Hopper worlds): the tableau form (lcp_ppt) executes fewer
     // instructions but its per-row exchange branches cost more fetch stalls than they save for a lone
     // warp per SM (58.6 vs 53.8 us / env step), so the branch-free masked-Cholesky form stays the default.
+    // (Also measured and rejected: stage 1 on a permuted leading block at half the register size — the
+    // permutation through thread-local index arrays and the second instantiation cost more than the smaller
+    // Cholesky saves: Hopper 65536 worlds 138 vs 118 us, HalfCheetah 16384 worlds 644 vs 560 us.)
 #if defined(DARTB_LCP_PPT)
 #define LCP_REG lcp_ppt
-#elif defined(DARTB_LCP_SPLIT)
-#define LCP_REG lcp_small2
 #else
 #define LCP_REG lcp_small
 #endif

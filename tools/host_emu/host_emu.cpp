@@ -159,9 +159,6 @@ static int run_lcp(int n, const double* A, const double* b, const double* lo, co
     else if (mode == 3) lcp_dantzig<R, NR>(n, a, xx, bb, l, h, fi);
     else if (mode == 4) ok = lcp_small<R, 4>(n, a, xx, bb, l, h, fi);
     else if (mode == 5) ok = lcp_small<R, 6>(n, a, xx, bb, l, h, fi);
-    else if (mode == 9) ok = lcp_small2<R, 4>(n, a, xx, bb, l, h, fi);
-    else if (mode == 10) ok = lcp_small2<R, 6>(n, a, xx, bb, l, h, fi);
-    else if (mode == 11) ok = lcp_small2<R, 8>(n, a, xx, bb, l, h, fi);
     else if (mode == 6) ok = lcp_ppt<R, 4>(n, a, xx, bb, l, h, fi);
     else if (mode == 7) ok = lcp_ppt<R, 6>(n, a, xx, bb, l, h, fi);
     else if (mode == 8) ok = lcp_ppt<R, 8>(n, a, xx, bb, l, h, fi);
