@@ -103,8 +103,10 @@ static int lower_into(dartb_engine* e) {
     static int forced_variant = -2;
     if (forced_variant < -1) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : -1; }
     const int want = e->variant_request >= 0 ? e->variant_request : forced_variant;
+    const bool coop_ok = !(res.t.fluid_force && res.m.ns > 0);   // no cooperative fluid kernel for topologies with capsules
     if (topo < 0 || res.m.any_coulomb || want == 1) e->variant = 1;
-    else if (want == 2) e->variant = 2;
+    else if (want == 2 && coop_ok) e->variant = 2;
+    else if (!coop_ok) e->variant = 0;
     else if (want == 0) e->variant = 0;
     else {
         // auto: the cooperative kernel while the batch leaves warp schedulers idle at one world per thread

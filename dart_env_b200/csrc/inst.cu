@@ -41,8 +41,12 @@ static int coop_warps() {   // warps per block (1, 2 or 4; DARTB_COOP_WARPS over
 static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a, const void* tab) {
     const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a.n + per_block - 1) / per_block;
     const CoopLane<T_, R_>* t = (const CoopLane<T_, R_>*)tab;
-    if (K.fluid_force) k_env_step_coop<T_, R_, true><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
-    else k_env_step_coop<T_, R_, false><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
+    // the fluid-force instantiation exists for capsule-free topologies only (the snake: the one task that has it);
+    // dartb.cu::lower_into keeps fluid tasks on other topologies on the per-thread kernels
+    if constexpr (T_::NS == 0) {
+        if (K.fluid_force) { k_env_step_coop<T_, R_, true><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t); return; }
+    }
+    k_env_step_coop<T_, R_, false><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
 }
 static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, const void* tab, int n, R_* q, R_* dq, const R_* tau, int lcp_mode,
                            int pgs_iters, const ContactSink<R_>& sink) {
