@@ -499,7 +499,6 @@ DEVI void coop_pgs(int l, int n, int nmax, const R (&A)[(NCx + Coop<T>::G - 1) /
 #pragma unroll
         for (int i = 0; i < NC; i++) {
             // the owner of row i updates x_i from the freshest values, then everyone learns it
-            constexpr int dummy = 0; (void)dummy;
             const int h = i / G;
             R xi = 0;
             if (l == i % G && i < n) {
