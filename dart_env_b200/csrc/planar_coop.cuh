@@ -611,7 +611,8 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         // (never reached by the in-scope tasks' normal operation) run the LCP in the mass-matrix precision.
         using RL = typename std::conditional<(NCx >= 16), RM, R>::type;
         const RL INFL = Num<RL>::inf();
-        RM Y[RPL][NB];
+        R Jf[RPL][NB];      // J_r (this lane's rows)
+        RM MJ[RPL][NB];     // M^-1 J_r^T
         RL bb[RPL], lo[RPL], hi[RPL];
         int fi[RPL], kind[RPL], rsrc[RPL];
         unsigned hin[RPL];
@@ -619,7 +620,7 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
         for (int h = 0; h < RPL; h++) {
             const int r = l + h * G;
             kind[h] = 0; rsrc[h] = 0; fi[h] = -1; bb[h] = 0; lo[h] = 0; hi[h] = 0; hin[h] = 3u;
-            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Y[h][j] = 0; });
+            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Jf[h][j] = 0; });
             if (r < n) {
                 kind[h] = rows->kind[r]; rsrc[h] = rows->src[r];
                 const unsigned anc = rows->anc[r];
@@ -634,7 +635,7 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
                         else Jv = Ugx[j] * w1 + Ugy[j] * w2;
                         if (!((anc >> j) & 1u)) Jv = 0;
                     } else Jv = (j == rsrc[h]) ? (R)1 : (R)0;
-                    Y[h][j] = Jv;
+                    Jf[h][j] = Jv;
                     vn += Jv * dqg[j];
                 });
                 bb[h] = (RL)(bias - vn);
@@ -642,22 +643,21 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
                 else if (kind[h] == 4) { lo[h] = -INFL; hi[h] = 0; }
                 else { lo[h] = -(RL)mu; hi[h] = (RL)mu; fi[h] = r - 1; hin[h] = (hint >> (2 * rsrc[h])) & 3u; }
             }
-            ltl_solve_t<T, RM>(Mf, Li, Y[h]);     // Y_r = L^-T J_r^T
+            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; MJ[h][j] = (RM)Jf[h][j]; });
+            ltl_solve_t<T, RM>(Mf, Li, MJ[h]);
+            ltl_solve<T, RM>(Mf, Li, MJ[h]);      // M^-1 J_r^T = L^-1 L^-T J_r^T  (DART: applyUnitImpulse + getVelocityChange)
         }
-        // A[r][s] = Y_r . Y_s (+ CFM on the diagonal).  The smallest class keeps every Y_s it fetched, so K7
-        // needs the impulses only (NC shuffles) instead of a NB-vector reduction over the group.
-        constexpr bool KEEPY = NCx <= 4;
-        RM Yall[KEEPY ? NC : 1][NB];
+        // A[r][s] = J_s . (M^-1 J_r^T) (+ CFM on the diagonal): the fp32 rows J_s travel by shuffles, the products
+        // accumulate in RM
         RL A[RPL][NC];
 #pragma unroll
         for (int s = 0; s < NC; s++) {
-            RM Ys[NB];
-            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Ys[j] = gshfl<G>(Y[s / G][j], s % G); });
-            if constexpr (KEEPY) { static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Yall[s][j] = Ys[j]; }); }
+            R Js[NB];
+            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; Js[j] = gshfl<G>(Jf[s / G][j], s % G); });
 #pragma unroll
             for (int h = 0; h < RPL; h++) {
                 RM v = 0;
-                static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; v += Y[h][j] * Ys[j]; });
+                static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; v += MJ[h][j] * (RM)Js[j]; });
                 if (s == l + h * G) v *= (RM)1 + (kind[h] <= 2 ? (RM)DK_CONTACT_CFM : (RM)DK_LIMIT_CFM);
                 A[h][s] = (RL)v;
             }
@@ -687,32 +687,15 @@ DEVI void coop_constraints(const PModel<R>& M, const CoopLane<T, R>& c, int gbas
                 for (int h = 0; h < RPL; h++) if (!ok) { x[h] = x2[h]; st[h] = 3u; }
             }
         }
-        // ---------------- K7: dq += L^-1 sum_r Y_r x_r
-        RM zs[NB];
-        if constexpr (KEEPY) {
-            RL xs_[NC];
-            CoopLcp<T, RL, NCx>::gather_rows(x, xs_, nmax);
-            // summed in the order of the group_sum butterfly of the larger classes (products rounded one by
-            // one, pairs (0,2) and (1,3) first), so a world's result does not depend on which class its warp
-            // neighbours put it in
-            static_assert(NC == 4, "the small class is 4 columns");
-            static_for<0, NB>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const RM p0 = coop_mul_rn(Yall[0][j], (RM)xs_[0]), p1 = coop_mul_rn(Yall[1][j], (RM)xs_[1]);
-                const RM p2 = coop_mul_rn(Yall[2][j], (RM)xs_[2]), p3 = coop_mul_rn(Yall[3][j], (RM)xs_[3]);
-                zs[j] = coop_add_rn(coop_add_rn(p0, p2), coop_add_rn(p1, p3));
-            });
-        } else {
-            static_for<0, NB>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                RM v = (l < n) ? coop_mul_rn(Y[0][j], (RM)x[0]) : (RM)0;
+        // ---------------- K7: dq += sum_r (M^-1 J_r^T) x_r: each row's contribution rounded to R, summed over the group
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            R v = (l < n) ? (R)(MJ[0][i] * (RM)x[0]) : (R)0;
 #pragma unroll
-                for (int h = 1; h < RPL; h++) if (l + h * G < n) v = coop_add_rn(v, coop_mul_rn(Y[h][j], (RM)x[h]));
-                zs[j] = group_sum<G>(v);
-            });
-        }
-        ltl_solve<T, RM>(Mf, Li, zs);
-        static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; if (l == i) dq += (R)zs[i]; });
+            for (int h = 1; h < RPL; h++) if (l + h * G < n) v = coop_add_rn(v, (R)(MJ[h][i] * (RM)x[h]));
+            const R d = group_sum<G>(v);
+            if (l == i) dq += d;
+        });
         // stick/slide sets of the friction rows for the next step
         {
             unsigned clr = 0, set = 0;
