@@ -16,11 +16,11 @@
 //       diagonal pivot of each joint, i.e. to diag(M); solved by the sparse L^T L factorisation
 //       (Featherstone's LTL: no fill-in for the tree), unrolled at compile time
 //   K4  capsule s vs ground box on lane s (the ODE walk of planar_kernels.cuh, one shape per lane)
-//   K5  rows compacted through shared memory; row r lives on lane r: J_r, Y_r = L^-T J_r^T,
-//       A[r][:] = Y_r . Y_s (Y_s fetched by shuffles), exactly J M^-1 J^T of DART's impulse tests
+//   K5  rows compacted through shared memory; row r lives on lane r: J_r, M^-1 J_r^T = L^-1 L^-T J_r^T,
+//       A[r][:] = J_s . (M^-1 J_r^T) with the fp32 rows J_s fetched by shuffles: DART's impulse tests
 //   K6  boxed LCP: the block-principal-pivoting iteration of planar_kernels.cuh::lcp_ppt with the
 //       tableau distributed one row per lane (exchange = one shuffle round + one FMA per column)
-//   K7  dq += L^-1 sum_r Y_r x_r ; q += dt dq
+//   K7  dq += sum_r (M^-1 J_r^T) x_r (group sum) ; q += dt dq
 // Mathematically the same step as planar_kernels.cuh::substep (ABA and M^-1 are the same linear
 // operator); tests hold both against the fp64 oracle.
 #pragma once
