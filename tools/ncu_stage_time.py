@@ -39,6 +39,12 @@ def region(line):
 
 lcp_lo = next(k + 1 for k, l in enumerate(src) if "struct CoopLcp" in l)
 lcp_hi = next(k + 1 for k, l in enumerate(src) if "DEVI void coop_pgs" in l)
+LCP_PATS = [("static DEVI void gather_rows", "gather_rows"), ("static DEVI bool exchange", "exchange"), ("static DEVI bool solve", "init"),
+            ("if (stage == 1) {", "stage-2 setup"), ("int best = NC + 1, tries = 3;", "iteration control"), ("unsigned flip = 0;", "flip ballots"),
+            ("while (__any_sync(COOP_FULL, flip != 0))", "exchange loop"), ("R z[RPL], zg[NC], y[RPL];", "z gather + matvec"),
+            ("const R xs = group_max<G>(axm)", "xs / S reductions"), ("unsigned badm = 0, nst[RPL];", "feasibility check + ballots"),
+            ("const int nbad = __popc(badm);", "set update"), ("// one round of iterative refinement", "refinement")]
+lcp_marks = sorted((k + 1, name) for k, l in enumerate(src) for pat, name in LCP_PATS if pat in l and lcp_lo <= k + 1 < lcp_hi)
 stage_of = {}
 infun, chain, pending = False, [], []
 ann = re.compile(r'//## File "([^"]+)", line (\d+)')
@@ -67,6 +73,12 @@ for l in sass:
                 break
         if in_lcp:
             st = "K6 LCP"
+            # finer: which part of CoopLcp (innermost line inside the struct)
+            for f, ln in chain:
+                if f == "planar_coop.cuh" and lcp_lo <= ln < lcp_hi:
+                    sub = [m[1] for m in lcp_marks if m[0] <= ln]
+                    st = "K6 LCP: " + (sub[-1] if sub else "gather_rows / exchange")
+                    break
         stage_of[off] = (st or "other", m.group(2).split()[0] if not m.group(2).startswith("@") else m.group(2).split()[1])
 rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                                                  capture_output=True, text=True).stdout)))
