@@ -80,3 +80,14 @@ def test_reset_noise_is_counter_based_and_bounded():
     assert u.min() >= -1.0 and u.max() < 1.0 and len(np.unique(u)) == len(u)
     assert orc.reset_uniform(7, 1, 2, 3) == orc.reset_uniform(7, 1, 2, 3)
     spec = SPECS["DartHopper-v1"]
+
+
+def test_pydart2_replay_script_reports_unavailable_cleanly():
+    """oracle/replay_with_pydart2.py is the pin against real pydart2 for whoever has it; here (no pydart2, no
+    DART) it must say so and exit 0 — and never mistake the oracle's own pydart2 shim for the real thing."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "oracle", "pydart2_shim"))
+    r = subprocess.run([_sys.executable, os.path.join(root, "oracle", "replay_with_pydart2.py")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "unavailable" in r.stdout, r.stdout + r.stderr
