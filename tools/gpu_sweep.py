@@ -69,6 +69,10 @@ elif mode == "big":   # per-thread kernels at their large-batch sizes
     for env_id, n in (("DartHopper-v1", 65536), ("DartHopper-v1", 16384), ("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384),
                       ("DartSnake7Link-v1", 32768)):
         cfgs.append((env_id, n, "128", "0"))
+elif mode == "xover":   # both forms right at the automatic crossover sizes
+    for env_id, n in (("DartHopper-v1", 4736), ("DartWalker2d-v1", 6144), ("DartHalfCheetah-v1", 12288), ("DartSnake7Link-v1", 2368)):
+        for v in ("0", "2"):
+            cfgs.append((env_id, n, "128", v))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):
