@@ -155,6 +155,21 @@ class DartEnv:
 
     # ------------------------------------------------------------------ reference surface
     @property
+    def dart_world(self):
+        """pydart2-shaped view of the batched world (dart_env.py:54-62): dt, step(), reset(), skeletons,
+        collision_result.contacts."""
+        if getattr(self, "_world_view", None) is None:
+            from .pydart_view import WorldView
+            self._world_view = WorldView(self)
+        return self._world_view
+
+    @property
+    def robot_skeleton(self):
+        """`self.robot_skeleton = self.dart_world.skeletons[-1]` (dart_env.py:62): q, dq, ndofs, set_positions,
+        set_velocities, set_forces, q_lower / q_upper, bodynodes[i].com() / to_world() / com_spatial_velocity() ..."""
+        return self.dart_world.robot
+
+    @property
     def dt(self):
         return self.model.dt * self.frame_skip
 

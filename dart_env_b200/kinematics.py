@@ -50,3 +50,43 @@ def body_point_world(model: Model, q: torch.Tensor, body: int, local=(0.0, 0.0, 
     R, p = body_transforms(model, q)
     loc = torch.tensor(np.asarray(local, dtype=np.float64), device=q.device)
     return (R[:, body] @ loc).reshape(q.shape[0], 3) + p[:, body]
+
+
+def body_com_world(model: Model, q: torch.Tensor) -> torch.Tensor:
+    """bodynodes[*].com() -> [N,nb,3]."""
+    R, p = body_transforms(model, q)
+    loc = torch.tensor(np.array([b.com for b in model.bodies], dtype=np.float64), device=q.device)   # [nb,3]
+    return (R @ loc[None, :, :, None]).squeeze(-1) + p
+
+
+def body_com_spatial_velocities(model: Model, q: torch.Tensor, dq: torch.Tensor) -> torch.Tensor:
+    """bodynodes[*].com_spatial_velocity() -> [N,nb,6] = [angular; linear velocity of the COM], world axes
+    (pydart2's default frames: relative to and expressed in the world)."""
+    n, dev, dt = q.shape[0], q.device, torch.float64
+    q, dq = q.to(dt), dq.to(dt)
+    R, p = body_transforms(model, q)
+    com = body_com_world(model, q)
+    W, V = [], []          # angular velocity and linear velocity of the body ORIGIN
+    for k, b in enumerate(model.bodies):
+        if b.parent >= 0:
+            wp, vp = W[b.parent], V[b.parent] + torch.cross(W[b.parent], p[:, k] - p[:, b.parent], dim=1)
+            Rp = R[:, b.parent]
+        else:
+            wp = torch.zeros((n, 3), dtype=dt, device=dev); vp = torch.zeros((n, 3), dtype=dt, device=dev)
+            Rp = torch.eye(3, dtype=dt, device=dev).expand(n, 3, 3)
+        w, v = wp, vp
+        if b.dof >= 0:
+            Tpj = torch.tensor(b.T_parent_joint, dtype=dt, device=dev)
+            axis_w = (Rp @ (Tpj[:3, :3] @ torch.tensor(b.axis, dtype=dt, device=dev)))          # joint axis, world axes
+            if b.joint_type == JOINT_REVOLUTE:
+                # the joint frame origin in the world: parent origin + Rp * Tpj.p ; the body origin turns about it
+                jo = p[:, b.parent] + (Rp @ Tpj[:3, 3]) if b.parent >= 0 else Tpj[:3, 3].expand(n, 3)
+                wj = axis_w * dq[:, b.dof, None]
+                w = wp + wj
+                v = vp + torch.cross(wj, p[:, k] - jo, dim=1)
+            elif b.joint_type == JOINT_PRISMATIC:
+                v = vp + axis_w * dq[:, b.dof, None]
+        W.append(w); V.append(v)
+    W, V = torch.stack(W, 1), torch.stack(V, 1)
+    vc = V + torch.cross(W, com - p, dim=2)
+    return torch.cat([W, vc], dim=2)
