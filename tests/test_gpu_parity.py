@@ -390,47 +390,47 @@ def test_rollout_statistics_match_oracle(models, env_id):
     assert abs(g_rew - o_rew) < 0.15 * max(1.0, abs(o_rew)), (g_rew, o_rew)
 
 
-def test_pydart2_shaped_views_match_the_oracle_shim(models):
+def test_pydart2_shaped_views_match_the_oracle(models):
     """env.dart_world / env.robot_skeleton answer the pydart2 calls the reference's env classes make
-     with the values the oracle's pydart2 shim gives for the same state."""
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, os.path.join(root, "oracle", "pydart2_shim"))
-    try:
-        import pydart2 as shim
-        env_id = "DartWalker2d-v1"
-        spec = SPECS[env_id]
-        env = _make(env_id, seed=0)
-        env.reset()
-        rs = env.robot_skeleton
-        assert rs.ndofs == 9 and rs.q.shape == (9,) and rs.dq.shape == (9,)
-        assert np.array_equal(rs.q_lower, models[env_id].q_lower()) and env.dart_world.dt == spec.dt
-        assert env.dart_world.skeletons[-1] is rs
-        rng = np.random.RandomState(0)
-        q = models[env_id].q_init() + rng.uniform(-0.2, 0.2, 9); dq = rng.uniform(-1, 1, 9)
-        q[1] += 0.3                                   # lifted off the ground: a contact-free comparison step
-        rs.set_positions(q); rs.set_velocities(dq)
-        assert np.allclose(rs.q, q, atol=1e-6) and np.allclose(rs.dq, dq, atol=1e-6)
-        from dart_env_b200.skel import find_asset
-        w = shim.World(spec.dt, find_asset(spec.skel))
-        sk = w.skeletons[-1]
-        sk.set_positions(rs.q); sk.set_velocities(rs.dq)
-        for i in (2, 5, 8):
-            assert np.allclose(rs.bodynodes[i].com(), sk.bodynodes[i].com(), atol=1e-9)
-            assert np.allclose(rs.bodynodes[i].to_world([0.1, -0.2, 0.0]), sk.bodynodes[i].to_world([0.1, -0.2, 0.0]), atol=1e-9)
-            assert np.allclose(rs.bodynodes[i].com_spatial_velocity(), sk.bodynodes[i].com_spatial_velocity(), atol=1e-9)
-        # set_forces + world.step() == one DART step of the shim (fp32 engine vs fp64 oracle)
-        tau = np.zeros(9); tau[3:] = rng.uniform(-20, 20, 6)
-        rs.set_forces(tau); env.dart_world.step()
-        sk.set_forces(tau); w.step()
-        assert np.allclose(rs.dq, sk.dq, rtol=2e-4, atol=2e-4) and np.allclose(rs.q, sk.q, atol=1e-5)
-        # falling onto the ground produces contacts with upward force
-        for _ in range(300):
-            env.dart_world.step()
-        cs = env.dart_world.collision_result.contacts
-        assert len(cs) >= 1 and all(c.force[1] >= -1e-3 for c in cs)
-        env.close()
-    finally:
-        sys.path.pop(0)
-        for k in [k for k in sys.modules if k == "pydart2" or k.startswith("pydart2.")]:
-            del sys.modules[k]
+    (q, dq, ndofs, set_positions / set_velocities / set_forces, q_lower, bodynodes[i].com() /
+    to_world() / com_spatial_velocity(), world.dt / step() / skeletons / collision_result.contacts) with the
+    oracle's values for the same state."""
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    spec = SPECS[env_id]
+    env = _make(env_id, seed=0)
+    env.reset()
+    rs = env.robot_skeleton
+    assert rs.ndofs == 9 and rs.q.shape == (9,) and rs.dq.shape == (9,)
+    assert np.array_equal(rs.q_lower, models[env_id].q_lower()) and env.dart_world.dt == spec.dt
+    assert env.dart_world.skeletons[-1] is rs
+    rng = np.random.RandomState(0)
+    q = models[env_id].q_init() + rng.uniform(-0.2, 0.2, 9); dq = rng.uniform(-1, 1, 9)
+    q[1] += 0.3                                   # lifted off the ground: a contact-free comparison step
+    rs.set_positions(q); rs.set_velocities(dq)
+    assert np.allclose(rs.q, q, atol=1e-6) and np.allclose(rs.dq, dq, atol=1e-6)
+    w = orc.OracleWorld(models[env_id])
+    w.set_state(rs.q, rs.dq)
+    loc = np.array([0.1, -0.2, 0.0])
+    for i in (2, 5, 8):
+        T = w.body_transform(i)
+        assert np.allclose(rs.bodynodes[i].com(), w.body_com(i), atol=1e-9)
+        assert np.allclose(rs.bodynodes[i].to_world(loc), T[:3, :3] @ loc + T[:3, 3], atol=1e-9)
+        assert np.allclose(rs.bodynodes[i].T, T, atol=1e-9)
+        assert np.allclose(rs.bodynodes[i].com_spatial_velocity(), w.body_com_spatial_velocity(i), atol=1e-9)
+    # set_forces + world.step() == one DART step of the oracle (fp32 engine vs fp64 oracle)
+    tau = np.zeros(9); tau[3:] = rng.uniform(-20, 20, 6)
+    rs.set_forces(tau); env.dart_world.step()
+    w.set_forces(tau); w.step()
+    oq, odq = w.get_state()
+    assert np.allclose(rs.dq, odq, rtol=2e-4, atol=2e-4) and np.allclose(rs.q, oq, atol=1e-5)
+    # falling onto the ground produces contacts with upward force
+    for _ in range(300):
+        env.dart_world.step()
+    cs = env.dart_world.collision_result.contacts
+    assert len(cs) >= 1 and all(c.force[1] >= -1e-3 for c in cs)
+    # batched env: leading [N] axis
+    benv = _make(env_id, num_envs=4, seed=0, output="numpy")
+    benv.reset()
+    assert benv.robot_skeleton.q.shape == (4, 9) and benv.robot_skeleton.bodynodes[2].com().shape == (4, 3)
+    env.close(); benv.close()
