@@ -12,7 +12,8 @@ from test_gpu_parity import (  # noqa: F401  (collected here, run with VARIANT =
     test_env_step_matches_reference_task_layer, test_reset_noise_bit_exact_and_sharding_independent,
     test_pgs_mode_matches_oracle_pgs, test_full_size_properties_hopper_4096, test_time_limit_truncation,
     test_gym_surface_single_env_types, test_contacts_readback_walker, test_full_size_properties_other_configs,
-    test_rollout_statistics_match_oracle, test_pydart2_shaped_views_match_the_oracle)
+    test_rollout_statistics_match_oracle, test_pydart2_shaped_views_match_the_oracle,
+    test_step_is_cuda_graph_capturable)
 
 pytestmark = pytest.mark.gpu
 

@@ -434,3 +434,45 @@ def test_pydart2_shaped_views_match_the_oracle(models):
     benv.reset()
     assert benv.robot_skeleton.q.shape == (4, 9) and benv.robot_skeleton.bodynodes[2].com().shape == (4, 3)
     env.close(); benv.close()
+
+
+def test_step_is_cuda_graph_capturable(models):
+    """dartb_step enqueues exactly one kernel on the caller's stream and never synchronises, so a caller can
+    capture it in a CUDA graph (e.g. together with its policy network) and replay it: bit-identical to eager."""
+    env_id, n = "DartHopper-v1", 512
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev); gen.manual_seed(2)
+    acts = [torch.rand((n, 3), generator=gen, device=dev) * 2 - 1 for _ in range(6)]
+
+    def fresh():
+        eng = _engine(models, env_id, n, seed=8)
+        obs = eng.reset()
+        rew = torch.empty((n,), dtype=torch.float32, device=dev); done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        return eng, obs, rew, done
+
+    eng, obs, rew, done = fresh()
+    for a in acts:
+        eng.step(a, obs, rew, done, True)
+    q_ref, dq_ref = eng.get_state()
+    obs_ref = obs.clone()
+    eng.close()
+
+    eng, obs, rew, done = fresh()
+    a_static = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+    a_static.copy_(acts[0])
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.step(a_static, obs, rew, done, True)          # warm-up on the side stream (step 0)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    a_static.copy_(acts[1])
+    with torch.cuda.graph(g):
+        eng.step(a_static, obs, rew, done, True)          # captured, not executed
+    for a in acts[1:]:
+        a_static.copy_(a)
+        g.replay()
+    torch.cuda.synchronize()
+    q, dq = eng.get_state()
+    assert torch.equal(q, q_ref) and torch.equal(dq, dq_ref) and torch.equal(obs, obs_ref)
+    eng.close()
