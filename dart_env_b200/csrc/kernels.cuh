@@ -10,6 +10,11 @@
 #include "planar_loop.cuh"
 #include "planar_coop.cuh"
 
+// resident blocks (of 128 threads) per SM the per-thread kernels are compiled for: 1 = up to 255 registers
+#ifndef DARTB_STEP_MIN_BLOCKS
+#define DARTB_STEP_MIN_BLOCKS 1
+#endif
+
 template <class T, typename R>
 DEVI void write_obs(const PModel<R>& M, const PTask<R>& K, const R (&q)[T::NB], const R (&dq)[T::NB], float* so) {
     constexpr int NB = T::NB;
@@ -70,7 +75,7 @@ DEVI void reset_state(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int6
 
 // ------------------------------------------------------------------------ env.step() kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -180,7 +185,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
 
 // ------------------------------------------------------------------------ reset kernel
 template <class T, typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
     extern __shared__ float smem[];
@@ -219,7 +224,7 @@ k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K,
 // ------------------------------------------------------------------------ single DART step kernel
 // exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175) with optional ext forces
 template <class T, typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_substep(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, const R* fext /*[n,nbd,3]*/,
           int lcp_mode, int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
     constexpr int NB = T::NB;
@@ -297,7 +302,7 @@ DEVI void reset_state_loop(const PModel<R>& M, const PTask<R>& K, uint64_t seed,
 }
 
 template <typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     extern __shared__ float smem[];
     const int nb = M.nb;
@@ -378,7 +383,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
 }
 
 template <typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     extern __shared__ float smem[];
     const int nb = M.nb;
@@ -410,7 +415,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
 }
 
 template <typename R>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in, const R* fext, int lcp_mode,
                int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
     const int nb = M.nb;
