@@ -46,6 +46,19 @@ __global__ void k_convert(size_t n, const S* src, D* dst) {
     if (k < n) dst[k] = (D)src[k];
 }
 
+// ------------------------------------------------------------------------ developer overrides (environment)
+// read once, through a C++11 function-local static (thread-safe initialisation): handles may be created from
+// several host threads
+struct EnvCfg {
+    int variant, block, wpw, zerocopy; long coop_max;
+    EnvCfg() {
+        auto geti = [](const char* k, long d) { const char* v = getenv(k); return v ? atol(v) : d; };
+        variant = (int)geti("DARTB_VARIANT", -1); block = (int)geti("DARTB_BLOCK", 0); wpw = (int)geti("DARTB_WPW", 0);
+        zerocopy = (int)geti("DARTB_ZEROCOPY", 1); coop_max = geti("DARTB_COOP_MAX_WORLDS", -1);
+    }
+};
+static const EnvCfg& envcfg() { static const EnvCfg c; return c; }
+
 // ------------------------------------------------------------------------ engine
 enum { TOPO_HOPPER = 0, TOPO_WALKER, TOPO_CHEETAH, TOPO_SNAKE, TOPO_COUNT };
 
@@ -69,6 +82,8 @@ struct dartb_engine {
     int wpw_request = 0;                      // worlds per warp of k_env_step, 0 = auto (wpw_for)
     void* coop_tab = nullptr; size_t coop_tab_bytes = 0; bool coop_tab_dirty = true;   // per-lane constants of the cooperative kernels
     int64_t launches = 0;
+    bool contacts = false;                    // DARTB_OPT_CONTACTS: the fused step records the last sub-step's contacts
+    bool contacts_valid = false;              // the contact buffers describe the last stepping call
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
     float* h_stage = nullptr; float* d_stage = nullptr; float* h_stage_dev = nullptr; size_t stage_floats = 0;
     const void* zc_h[3] = {nullptr, nullptr, nullptr}; void* zc_d[3] = {nullptr, nullptr, nullptr};   // zero-copy output aliases
@@ -100,8 +115,7 @@ static int lower_into(dartb_engine* e) {
     for (int i = 0; i < res.m.nb; i++) nlim += res.m.limited[i] ? 1 : 0;
     int topo = pick_topo(res.signature, nlim);
     if (res.m.ns > LOOP_MAXS || res.m.nb > LOOP_MAXB) return fail("model too large for the planar kernels");
-    static int forced_variant = -2;
-    if (forced_variant < -1) { const char* ev = getenv("DARTB_VARIANT"); forced_variant = ev ? atoi(ev) : -1; }
+    const int forced_variant = envcfg().variant;
     const int want = e->variant_request >= 0 ? e->variant_request : forced_variant;
     const bool coop_ok = !(res.t.fluid_force && res.m.ns > 0);   // no cooperative fluid kernel for topologies with capsules
     if (topo < 0 || res.m.any_coulomb || want == 1) e->variant = 1;
@@ -114,9 +128,7 @@ static int lower_into(dartb_engine* e) {
         // Crossovers measured on B200 (gpurun_out/sweep_coop*.log, us per env step, cooperative vs per-thread):
         //   Hopper      4096: 38 vs 54    6144: 62 vs 54      Walker2d   4096: 107 vs 135   8192: 196 vs 156
         //   HalfCheetah 8192: 340 vs 489  12288: 497 vs 492   Snake7Link 2048: 34 vs 39     4096: 59 vs 42
-        static long coop_max = -2;
-        if (coop_max < -1) { const char* ev = getenv("DARTB_COOP_MAX_WORLDS"); coop_max = ev ? atol(ev) : -1; }
-        long lim = coop_max;
+        long lim = envcfg().coop_max;
         if (lim < 0) lim = topo == TOPO_HOPPER ? 4736 : (topo == TOPO_WALKER ? 6144 : (topo == TOPO_CHEETAH ? 12288 : 2368));
         e->variant = (e->n <= lim) ? 2 : 0;
     }
@@ -147,8 +159,7 @@ template <> struct Sel<double> {
 static int block_for(int n) {
     // One warp per SM cannot hide instruction-fetch latency of the unrolled stepper (ncu: stall_no_inst
     // dominant); several warps per SM share the instruction stream.  DARTB_BLOCK overrides (experiments).
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("DARTB_BLOCK"); forced = e ? atoi(e) : 0; }
+    const int forced = envcfg().block;
     if (forced >= 32 && forced <= 128 && forced % 32 == 0) return forced;
     return n <= 148 * 32 * 4 ? 32 : (n <= 148 * 64 * 8 ? 64 : 128);
 }
@@ -159,8 +170,7 @@ static int block_for(int n) {
 // worlds per warp = a shorter union path, and the idle schedulers run them concurrently.
 // DARTB_WPW / DARTB_OPT_WORLDS_PER_WARP override.
 static int wpw_for(const dartb_engine* e) {
-    static int forced = -1;
-    if (forced < 0) { const char* ev = getenv("DARTB_WPW"); forced = ev ? atoi(ev) : 0; }
+    const int forced = envcfg().wpw;
     int w = e->wpw_request > 0 ? e->wpw_request : forced;
     if (w >= 1 && w <= 32) return w;
     // one warp per scheduler: measured (gpurun_out/sweep_wpw.log) a second narrower warp per scheduler
@@ -180,7 +190,8 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.hint = e->hint;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset;
-    a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; a.sink.maxc = e->max_contacts;
+    if (e->contacts) { a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; }
+    a.sink.maxc = e->max_contacts;
     return a;
 }
 
@@ -230,9 +241,12 @@ static int coop_table_sync(dartb_engine* e, cudaStream_t st) {
 
 template <typename R>
 static int launch_step(dartb_engine* e, const float* action, float* obs, float* reward, uint8_t* done, int auto_reset,
-                       cudaStream_t st) {
+                       cudaStream_t st, double* reward64 = nullptr, uint8_t* truncated = nullptr) {
     StepArgs<R> a = make_args<R>(e);
     a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.auto_reset = auto_reset;
+    a.reward64 = reward64;
+    if (truncated) a.truncated = truncated;
+    e->contacts_valid = e->contacts;
     if (e->variant == 2) {
         if (coop_table_sync<R>(e, st)) return 1;
         LTab<R>::get(e).step_coop(st, Sel<R>::m(e), Sel<R>::t(e), a, e->coop_tab);
@@ -255,6 +269,7 @@ template <typename R>
 static int launch_reset(dartb_engine* e, const uint8_t* mask, float* obs, cudaStream_t st) {
     StepArgs<R> a = make_args<R>(e);
     a.mask = mask; a.obs = obs;
+    a.sink.count = e->ccount;   // a reset world has no contacts (world.reset() clears collision_result)
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
     const PTask<R>& K = Sel<R>::t(e);
     const size_t shm = (size_t)(bs / 32) * 32 * K.n_obs * sizeof(float);
@@ -268,6 +283,7 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
     ContactSink<R> sink;
     sink.count = e->ccount; sink.body = e->cbody; sink.data = e->cdata; sink.maxc = e->max_contacts;
     const int bs = block_for(e->n), grid = (e->n + bs - 1) / bs;
+    e->contacts_valid = true;   // the literal World.step() always refreshes collision_result
     if (e->variant == 2 && !fext) {
         if (coop_table_sync<R>(e, st)) return 1;
         LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->coop_tab, e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
@@ -319,14 +335,15 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
         if (f64) {
             std::vector<double> hq((size_t)n * nd), hv((size_t)n * nd);
             for (int d = 0; d < nd; d++) for (int w = 0; w < n; w++) { hq[(size_t)d * n + w] = e->md.qinit[d]; hv[(size_t)d * n + w] = e->md.dqinit[d]; }
-            cudaMemcpy(e->q, hq.data(), hq.size() * 8, cudaMemcpyHostToDevice);
-            cudaMemcpy(e->dq, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice);
+            err = cudaMemcpy(e->q, hq.data(), hq.size() * 8, cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) err = cudaMemcpy(e->dq, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice);
         } else {
             std::vector<float> hq((size_t)n * nd), hv((size_t)n * nd);
             for (int d = 0; d < nd; d++) for (int w = 0; w < n; w++) { hq[(size_t)d * n + w] = e->mf.qinit[d]; hv[(size_t)d * n + w] = e->mf.dqinit[d]; }
-            cudaMemcpy(e->q, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice);
-            cudaMemcpy(e->dq, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice);
+            err = cudaMemcpy(e->q, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) err = cudaMemcpy(e->dq, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice);
         }
+        if (err != cudaSuccess) { dartb_destroy(e); *out = nullptr; return fail(std::string("cudaMemcpy (initial state): ") + cudaGetErrorString(err)); }
     }
     return 0;
 }
@@ -408,6 +425,9 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
         case DARTB_OPT_WORLDS_PER_WARP:
             if (value < 0 || value > 32) return fail("worlds per warp must be 0 (auto) or 1..32");
             e->wpw_request = (int)value; return 0;
+        case DARTB_OPT_CONTACTS:
+            if (value != 0 && value != 1) return fail("contacts option must be 0 or 1");
+            e->contacts = value != 0; return 0;
         case DARTB_OPT_MAX_EPISODE_STEPS:
             if (value < 0) return fail("bad max_episode_steps");
             e->max_episode_steps = (int)value; return 0;
@@ -493,9 +513,7 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     const size_t need = fa + fo + fr + fd;
     if (ensure_stage(e, need)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    static int zc_env = -1;
-    if (zc_env < 0) { const char* ev = getenv("DARTB_ZEROCOPY"); zc_env = ev ? atoi(ev) : 1; }
-    if (zc_env && e->h_stage_dev) {
+    if (envcfg().zerocopy && e->h_stage_dev) {
         // Zero-copy: the step kernel reads the actions from, and writes obs / reward / done to, page-locked
         // host memory over PCIe itself (coalesced 128 B lines through its shared-memory staging), so the
         // whole host step is ONE launch + ONE sync: no memcpy nodes (each costs ~5 us of latency, more than
@@ -556,11 +574,28 @@ int dartb_step_host_gym(dartb_handle_t e, const float* h_action, float* obs_out,
     if (e->task.n_obs == 0) return fail("physics-only handle: no task layer configured (use dartb_substep)");
     const int n = e->n, na = e->task.n_act, no = e->task.n_obs;
     const size_t fa = (size_t)n * na, fo = (size_t)n * no, fr = (size_t)n, fd = ((size_t)n + 3) / 4;
-    {
-        DeviceGuard g(e->device);
-        if (ensure_stage(e, fa + fo + fr + fd)) return 1;
+    DeviceGuard g(e->device);
+    if (ensure_stage(e, fa + fo + fr + fd)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (envcfg().zerocopy && e->h_stage_dev) {
+        // Page-locked outputs (the DartEnv wrapper hands out arrays of its pinned pool): the kernel itself writes the
+        // reference's return types (float32 obs, float64 rewards, bool dones / truncated flags) over PCIe: ONE launch
+        // and ONE sync per env.step(), no conversion pass, no memcpy.
+        float* o_dev = (float*)mapped_alias(obs_out);
+        double* r_dev = (double*)mapped_alias(reward_out);
+        uint8_t* d_dev = (uint8_t*)mapped_alias(done_out);
+        uint8_t* t_dev = truncated_out ? (uint8_t*)mapped_alias(truncated_out) : nullptr;
+        if (o_dev && r_dev && d_dev && (t_dev || !truncated_out)) {
+            const float* a_dev = (const float*)mapped_alias(h_action);
+            if (!a_dev) { std::memcpy(e->h_stage, h_action, fa * 4); a_dev = e->h_stage_dev; }
+            int rc = e->f64 ? launch_step<double>(e, a_dev, o_dev, nullptr, d_dev, auto_reset, st, r_dev, t_dev)
+                            : launch_step<float>(e, a_dev, o_dev, nullptr, d_dev, auto_reset, st, r_dev, t_dev);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(st));
+            return 0;
+        }
     }
-    // the kernel writes into the page-locked staging block (zero-copy); the conversion to the reference's
+    // pageable outputs: the kernel writes into the page-locked staging block; the conversion to the reference's
     // return types (gym/vector/sync_vector_env.py:44-47: float64 rewards, bool dones) happens here, in one pass
     float* so = e->h_stage + fa;
     float* sr = so + fo;
@@ -602,6 +637,8 @@ int dartb_substep_f64(dartb_handle_t e, const double* d_tau, const double* d_fex
 
 int dartb_get_contacts(dartb_handle_t e, int32_t* d_count, int32_t* d_body, float* d_data, void* stream) {
     if (!e) return fail("null handle");
+    if (!e->contacts_valid)
+        return fail("contact read-back of the fused step is off: dartb_set_option(h, DARTB_OPT_CONTACTS, 1) before stepping");
     DeviceGuard g(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_count) CK(cudaMemcpyAsync(d_count, e->ccount, 4 * (size_t)e->n, cudaMemcpyDeviceToDevice, st));

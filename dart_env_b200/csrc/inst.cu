@@ -22,7 +22,8 @@ static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, in
 #else
 typedef INST_TOPO T_;
 static void l_step(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
-    k_env_step<T_, R_><<<grid, bs, shm, st>>>(M, K, a);
+    if (K.fluid_force) k_env_step<T_, R_, true><<<grid, bs, shm, st>>>(M, K, a);
+    else k_env_step<T_, R_, false><<<grid, bs, shm, st>>>(M, K, a);
 }
 static void l_reset(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
     k_reset<T_, R_><<<grid, bs, shm, st>>>(M, K, a);

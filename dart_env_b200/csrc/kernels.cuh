@@ -74,7 +74,9 @@ DEVI void reset_state(const PModel<R>& M, const PTask<R>& K, uint64_t seed, int6
 }
 
 // ------------------------------------------------------------------------ env.step() kernel
-template <class T, typename R>
+// FLUID (snake_7link.py:35-47) is a template parameter so that the contact topologies do not carry a second,
+// never-executed copy of the whole DART step (r1: 48.6 k SASS instructions per kernel, half of them that copy)
+template <class T, typename R, bool FLUID>
 __global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
     constexpr int NB = T::NB;
@@ -115,14 +117,13 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     __syncwarp();
 
     const R posbefore = q[0];
-    const ContactSink<R>* sink = &a.sink;
+    // contact read-back is opt-in (DARTB_OPT_CONTACTS): 356 B per world, more than the rest of the step's HBM traffic
+    const ContactSink<R>* sink = a.sink.count ? &a.sink : nullptr;
     uint64_t hint = active ? a.hint[w] : ~(uint64_t)0;
+#pragma unroll 1
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? sink : nullptr;
-        if (K.fluid_force)
-            substep<T, R, false, true>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w, hint);
-        else
-            substep<T, R, false, false>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, a.lcp_mode, a.pgs_iters, sk, w, hint);
+        substep<T, R, false, FLUID>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w, hint);
     }
     // reward / done (hopper.py:36-65, walker2d.py:22-65, half_cheetah.py:40-77, snake_7link.py:68-87)
     const R ang = q[2];
@@ -177,8 +178,11 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
             a.q[(size_t)i * a.n + w] = q[i];
             a.dq[(size_t)i * a.n + w] = dq[i];
         });
-        a.reward[w] = (float)r;
-        a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
+        else {
+            a.reward[w] = (float)r;
+            a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        }
         if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
     }
 }
@@ -332,7 +336,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     __syncwarp();
     const R posbefore = q[0];
     for (int f = 0; f < K.frame_skip; f++) {
-        const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? &a.sink : nullptr;
+        const ContactSink<R>* sk = (active && f == K.frame_skip - 1 && a.sink.count) ? &a.sink : nullptr;
         substep_loop<R>(M, q, dq, tau, false, tau, tau, tau, K.fluid_force != 0, K.fluid_offset, K.fluid_coef, a.lcp_mode,
                         a.pgs_iters, sk, w);
     }
@@ -376,8 +380,11 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
     if (active) {
         for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
-        a.reward[w] = (float)r;
-        a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
+        else {
+            a.reward[w] = (float)r;
+            a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        }
         if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
     }
 }

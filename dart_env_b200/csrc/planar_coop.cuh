@@ -1111,8 +1111,11 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     }
     if (mine) { a.q[(size_t)l * a.n + w] = q; a.dq[(size_t)l * a.n + w] = dq; }
     if (wactive && l == 0) {
-        a.reward[w] = (float)r;
-        a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
+        else {
+            a.reward[w] = (float)r;
+            a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        }
         if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
     }
 }

@@ -155,6 +155,12 @@ template <> struct Num<double> {
 #define DK_FRICTION_THRESHOLD 1e-3
 #define DK_CONTACT_EPS 1e-6
 
+// exact-LCP form of the per-thread kernels: 0 = register block pivoting per size class (lcp_small<4/6/8>),
+// 1 = thread-local block pivoting (lcp_bpp_local), 2 = compact rolled tableau (lcp_ppt_loop)
+#ifndef DARTB_LCP_FORM
+#define DARTB_LCP_FORM 0
+#endif
+
 // ------------------------------------------------------------------------ Philox4x32-10
 // identical to oracle/dart_oracle.c::orc_reset_uniform so reset noise is bit-identical
 DEVI void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -178,8 +184,13 @@ DEVI float reset_uniform(uint64_t seed, int64_t world, uint32_t episode, int i) 
 // ------------------------------------------------------------------------ K4: segment vs box (2-D)
 // ODE dClosestLineBoxPoints restricted to the plane (the out-of-plane axis has v = 0, region 0).
 // Exact minimiser of the convex piecewise-quadratic distance along p1->p2; ties -> t = 0 (p1).
+#if defined(DARTB_NOINLINE_CLOSEST) && !defined(DARTB_HOST_EMU)
+#define CLOSEST_DECL __device__ __noinline__
+#else
+#define CLOSEST_DECL DEVI
+#endif
 template <typename R>
-DEVI void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R hy, R& lx, R& ly, R& ddx, R& ddy) {
+CLOSEST_DECL void closest_segment_box2(R p1x, R p1y, R p2x, R p2y, R cx, R cy, R hx, R hy, R& lx, R& ly, R& ddx, R& ddy) {
     R s[2] = {p1x - cx, p1y - cy}, v[2] = {p2x - p1x, p2y - p1y}, sg[2], v2[2], ta[2];
     const R h[2] = {hx, hy};
     const R dvx = v[0], dvy = v[1];
@@ -797,6 +808,143 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
     return true;
 }
 
+// ------------------------------------------------------------------------ K6 compact path: tableau in loops
+// lcp_ppt's iteration (same sets visited, same rounding-aware tests, same two-stage friction bounds and
+// refinement) written as rolled loops over a thread-local tableau of stride n.  ~400 SASS instructions
+// for any n <= NR, against ~5 k per register size class of lcp_small: the large-batch per-thread kernels
+// are bound by instruction fetch (ncu r1: no_inst 47-55 % with the unrolled forms), and a solve that
+// stays inside the L0/L1.5 instruction caches costs less than one that executes fewer, colder instructions.
+template <typename R>
+DEVI unsigned set2(uint64_t v, int i) { return (unsigned)(v >> (2 * i)) & 3u; }
+DEVI uint64_t put2(uint64_t v, int i, unsigned s) { return (v & ~((uint64_t)3 << (2 * i))) | ((uint64_t)s << (2 * i)); }
+
+template <typename R, int NR>
+DEVI bool lcp_ppt_loop(int n, const R* A, R* x, const R* b, const R* lo_in, const R* hi_in, const int* fidx,
+                       const uint8_t* hin = nullptr, uint8_t* sout = nullptr) {
+    R T[NR * NR], lo[NR], hi[NR], sd[NR], z[NR], y[NR];
+    uint64_t cur = 0, st = 0;   // 2 bits per row: 0 free, 1 at lo, 2 at hi, 3 fixed at 0 (cur: what the tableau represents)
+    const R INF = Num<R>::inf();
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        lo[i] = lo_in[i]; hi[i] = hi_in[i]; x[i] = 0;
+#pragma unroll 1
+        for (int j = 0; j < n; j++) T[i * n + j] = A[i * n + j];
+        const R d = A[i * n + i];
+        sd[i] = Num<R>::sqrt_(d);
+        unsigned s = 0, c = 3;
+        if (!(d > Num<R>::inert())) s = 3;                            // inert row
+        else if (fidx[i] >= 0) s = 3;                                  // friction rows wait for stage 2
+        else if (lo[i] == 0 && hi[i] == INF) { s = b[i] > 0 ? 0u : 1u; c = 1; }
+        else if (hi[i] == 0 && lo[i] == -INF) { s = b[i] < 0 ? 0u : 2u; c = 2; }
+        st = put2(st, i, s); cur = put2(cur, i, c);                    // the tableau starts as A itself: every row bound
+    }
+#pragma unroll 1
+    for (int stage = 0; stage < 2; stage++) {
+        if (stage == 1) {
+            bool any = false;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) {
+                if (fidx[i] >= 0 && T[i * n + i] > Num<R>::inert()) {   // still bound: T_ii is A_ii's Schur complement > 0
+                    const R h = Num<R>::abs_(hi_in[i] * x[fidx[i]]);
+                    hi[i] = h; lo[i] = -h;
+                    const unsigned hh = hin ? hin[i] : 3u;
+                    unsigned s = 3;
+                    if (h != 0) { any = true; s = hh < 3u ? hh : 0u; }   // hinted set, else free (sticking)
+                    st = put2(st, i, s);
+                }
+            }
+            if (!any) break;
+        }
+        int best = n + 1, tries = 3;
+        bool done = false;
+#pragma unroll 1
+        for (int it = 0; it < 6 + 3 * n && !done; it++) {
+            // bring the tableau to the set `st`: one principal exchange per row whose free/bound status differs
+#pragma unroll 1
+            for (int k = 0; k < n; k++) {
+                if ((set2<R>(st, k) == 0) == (set2<R>(cur, k) == 0)) continue;
+                const R d = T[k * n + k];
+                if (!(d > 0)) return false;
+                const R p = Num<R>::rcp_(d);
+#pragma unroll 1
+                for (int i = 0; i < n; i++) {
+                    if (i == k) continue;
+                    const R c = T[i * n + k];
+#pragma unroll 1
+                    for (int j = 0; j < n; j++) if (j != k) T[i * n + j] -= c * (T[k * n + j] * p);
+                    T[i * n + k] = c * p;
+                }
+#pragma unroll 1
+                for (int j = 0; j < n; j++) if (j != k) T[k * n + j] = -(T[k * n + j] * p);
+                T[k * n + k] = p;
+            }
+            cur = st;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) {
+                const unsigned si = set2<R>(st, i);
+                z[i] = si == 0 ? b[i] : (si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0));
+            }
+            R xs = 0, S = 0;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) {
+                R s = 0;
+#pragma unroll 1
+                for (int j = 0; j < n; j++) s += T[i * n + j] * z[j];
+                y[i] = s;
+                x[i] = set2<R>(st, i) == 0 ? s : z[i];
+                const R ax = Num<R>::abs_(x[i]);
+                xs = ax > xs ? ax : xs;
+                S += sd[i] * ax;
+            }
+            const R tx = Num<R>::lcp_tol() * xs;
+            uint64_t nst = st;
+            int nbad = 0, last = -1;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) {
+                const unsigned si = set2<R>(st, i);
+                if (si == 3) continue;
+                if (si == 0) {
+                    if (x[i] < lo[i] - tx) { nbad++; last = i; nst = put2(nst, i, 1); }
+                    else if (x[i] > hi[i] + tx) { nbad++; last = i; nst = put2(nst, i, 2); }
+                } else {
+                    const R w = y[i] - b[i];
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
+                    if (((si == 1 && w < -tw) || (si == 2 && w > tw)) && lo[i] < hi[i]) { nbad++; last = i; nst = put2(nst, i, 0); }
+                }
+            }
+            EMU_COUNT(4, 1);
+            if (nbad == 0) { done = true; break; }
+            if (nbad < best) { best = nbad; tries = 3; st = nst; }
+            else if (tries > 0) { tries--; st = nst; }
+            else st = put2(st, last, set2<R>(nst, last));   // Murty: flip only the highest-index infeasible row
+        }
+        if (!done) return false;
+        // one round of iterative refinement against A itself (see lcp_ppt)
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            R s = 0;
+            if (set2<R>(st, i) == 0) {
+                s = b[i];
+#pragma unroll 1
+                for (int j = 0; j < n; j++) s -= A[i * n + j] * x[j];
+            }
+            z[i] = s;
+        }
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            if (set2<R>(st, i) != 0) continue;
+            R s = 0;
+#pragma unroll 1
+            for (int j = 0; j < n; j++) s += T[i * n + j] * z[j];
+            y[i] = s;
+        }
+#pragma unroll 1
+        for (int i = 0; i < n; i++) if (set2<R>(st, i) == 0) x[i] += y[i];
+    }
+    if (sout) for (int i = 0; i < n; i++) sout[i] = (uint8_t)set2<R>(st, i);
+    return true;
+}
+
 // exact LCP dispatch.  The size class is chosen per WARP (max n over the lanes that have rows), so
 // a warp executes ONE code path instead of one per distinct n: register block pivoting for
 // n <= 4 / 6 / 8, the thread-local block pivoting above that, Dantzig only if pivoting fails.
@@ -818,11 +966,20 @@ DEVI void lcp_exact(int n, const R* A, R* x, const R* b, R* lo, R* hi, const int
 #else
 #define LCP_REG lcp_small
 #endif
+#if DARTB_LCP_FORM == 2
+    // (n > 8: six or more capsules on the ground, A rank-deficient up to the CFM: the Gauss-Jordan tableau
+    // loses ~1e-3 there in fp32, the Cholesky-based pivoting below does not)
+    if (n <= 8) { ok = lcp_ppt_loop<R, NR>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
+    (void)nmax;
+#elif DARTB_LCP_FORM == 1
+    (void)nmax;
+#else
     if (nmax <= 4) { ok = LCP_REG<R, 4>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (nmax <= 6 && NR > 4) { ok = LCP_REG<R, 6>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(1, 1); }
     else if (NR > 6) {
         if (n <= 8) { ok = LCP_REG<R, 8>(n, A, x, b, lo, hi, fidx, hin, sout); if (ok) EMU_COUNT(2, 1); }
     }
+#endif
 #undef LCP_REG
     if (!ok) {
         if (sout) for (int i = 0; i < n; i++) sout[i] = 3;
@@ -874,6 +1031,8 @@ struct StepArgs {
     float* obs;          // [n, n_obs]
     float* reward;       // [n]
     uint8_t* done;       // [n]
+    double* reward64;    // gym return types (sync_vector_env.py:44-47): when set, rewards go HERE as float64 and `done`
+                         // receives plain 0/1 bools (the truncation flag only in `truncated`)
     const uint8_t* mask; // reset mask (k_reset) or null
     int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
     int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Optional, Sequence
 
 import numpy as np
@@ -29,6 +30,54 @@ from .skel import load_model
 from .spaces import Box, batch_space
 
 
+class _PinnedOutPool:
+    """Output arrays of the batched host path.  VectorEnv(copy=True) hands the caller arrays it may keep
+    (gym/vector/sync_vector_env.py:44-47,83); here the step kernel writes the reference's return types (float32 obs,
+    float64 rewards, bool dones) straight into page-locked numpy arrays over PCIe, so "a fresh copy" is a slot of this
+    pool that nobody references any more (CPython refcounts: any array or view the caller still holds keeps its slot
+    out of circulation).  No np.empty, no memcpy, no conversion pass per step."""
+
+    def __init__(self, n: int, n_obs: int, with_trunc: bool, max_slots: int = 64):
+        self.n, self.n_obs, self.with_trunc, self.max_slots = n, n_obs, with_trunc, max_slots
+        a16 = lambda v: (v + 15) // 16 * 16
+        self.off_rew = a16(n * n_obs * 4)
+        self.off_done = self.off_rew + a16(n * 8)
+        self.off_trunc = self.off_done + a16(n)
+        self.nbytes = self.off_trunc + (a16(n) if with_trunc else 0)
+        self.slots = []
+        self._next = 0
+
+    def _new_slot(self):
+        t = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        base = (C.c_char * self.nbytes).from_address(t.data_ptr())
+        n, no = self.n, self.n_obs
+        obs1 = np.frombuffer(base, dtype=np.float32, count=n * no, offset=0)
+        obs = obs1.reshape(n, no)
+        rew = np.frombuffer(base, dtype=np.float64, count=n, offset=self.off_rew)
+        done = np.frombuffer(base, dtype=np.bool_, count=n, offset=self.off_done)
+        trunc = np.frombuffer(base, dtype=np.bool_, count=n, offset=self.off_trunc) if self.with_trunc else None
+        p = t.data_ptr()
+        ptrs = (C.c_void_p(p), C.c_void_p(p + self.off_rew), C.c_void_p(p + self.off_done),
+                C.c_void_p(p + self.off_trunc) if self.with_trunc else None)
+        watched = [a for a in (obs1, obs, rew, done, trunc) if a is not None]
+        slot = {"keep": (t, base), "obs": obs, "rew": rew, "done": done, "trunc": trunc, "ptrs": ptrs, "watched": watched}
+        slot["idle"] = [sys.getrefcount(a) for a in watched]
+        self.slots.append(slot)
+        return slot
+
+    def take(self):
+        """a slot whose arrays nobody outside this pool references, or None when max_slots are all held"""
+        ns = len(self.slots)
+        for k in range(ns):
+            slot = self.slots[(self._next + k) % ns]
+            if [sys.getrefcount(a) for a in slot["watched"]] == slot["idle"]:
+                self._next = (self._next + k + 1) % ns
+                return slot
+        if ns < self.max_slots:
+            return self._new_slot()
+        return None
+
+
 class DartEnv:
     """Superclass for all (batched) Dart environments."""
 
@@ -39,7 +88,7 @@ class DartEnv:
                  task: Optional[Task] = None, num_envs: int = 1, batched: Optional[bool] = None, output: str = "torch",
                  device: int = 0, seed: Optional[int] = None, world_offset: int = 0, auto_reset: Optional[bool] = None,
                  max_episode_steps: int = 0, friction_all: Optional[float] = None, f64: bool = False,
-                 collidable: bool = True, copy: bool = True, kernel_variant: Optional[int] = None):
+                 collidable: bool = True, copy: bool = True, kernel_variant: Optional[int] = None, contacts: bool = False):
         assert obs_type in ("parameter", "image")
         assert action_type in ("continuous", "discrete")
         if obs_type == "image":
@@ -89,6 +138,7 @@ class DartEnv:
         self._device_index = device
         self._f64 = f64
         self._kernel_variant = kernel_variant
+        self._contacts = bool(contacts)   # record collision_result.contacts in the fused step (walker2d.py:38-41)
 
         self.action_space = Box(np.asarray(action_bounds[1], dtype=np.float64), np.asarray(action_bounds[0], dtype=np.float64))
         high = np.inf * np.ones(self.obs_dim)
@@ -112,6 +162,8 @@ class DartEnv:
                              world_offset=self.world_offset, f64=self._f64, kernel_variant=self._kernel_variant)
         if getattr(self, "max_episode_steps", 0):
             self.engine.set_max_episode_steps(self.max_episode_steps)
+        if self._contacts:
+            self.engine.set_contacts(True)
         dev, n = self.engine.device, self.num_envs
         self._obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
         self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -127,6 +179,7 @@ class DartEnv:
         self._n_rew = torch.empty((n,), dtype=torch.float32).pin_memory().numpy()
         self._n_done = torch.empty((n,), dtype=torch.uint8).pin_memory().numpy()
         self._c_obs, self._c_rew, self._c_done = (C.c_void_p(x.ctypes.data) for x in (self._n_obs, self._n_rew, self._n_done))
+        self._pool = None   # pinned output slots of the batched host path (built on first use)
 
     @property
     def max_episode_steps(self):
@@ -247,7 +300,17 @@ class DartEnv:
                 act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
             eng = self.engine
             if self.batched and self.copy:
-                # reference return types in one library call: fresh float32 obs, float64 rewards, bool dones
+                # reference return types in one library call, written by the kernel into an unreferenced pinned slot
+                if self._pool is None or self._pool.with_trunc != bool(self._max_episode_steps):
+                    self._pool = _PinnedOutPool(self.num_envs, self.obs_dim, bool(self._max_episode_steps))
+                slot = self._pool.take()
+                if slot is not None:
+                    po, pr, pd, pt = slot["ptrs"]
+                    rc = eng.L.dartb_step_host_gym(eng.h, act.ctypes.data, po, pr, pd, pt, int(self.auto_reset), eng._stream())
+                    if rc:
+                        capi.check(rc)
+                    return slot["obs"], slot["rew"], slot["done"], ({"TimeLimit.truncated": slot["trunc"]} if pt is not None else {})
+                # (every slot is still held by the caller: plain pageable arrays, filled from the staging block)
                 n = self.num_envs
                 obs = np.empty((n, self.obs_dim), dtype=np.float32)
                 rew = np.empty((n,), dtype=np.float64)
@@ -310,7 +373,8 @@ class DartEnv:
         pass
 
     def contacts(self):
-        """world.collision_result.contacts of the last sub-step: (count[N], body[N,C], data[N,C,10])."""
+        """world.collision_result.contacts of the last sub-step: (count[N], body[N,C], data[N,C,10]).
+        After a fused step() this needs DartEnv(contacts=True); do_simulation() always records."""
         return self.engine.contacts()
 
     def __del__(self):

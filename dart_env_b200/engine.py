@@ -13,6 +13,8 @@ from .skel import Model
 
 OPT_MAX_EPISODE_STEPS = 4
 OPT_KERNEL_VARIANT = 5   # -1 auto, 0 one world per thread, 1 loop / generic, 2 lane-cooperative
+OPT_WORLDS_PER_WARP = 6
+OPT_CONTACTS = 7         # 1: the fused step records collision_result.contacts of its last sub-step
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -67,6 +69,11 @@ class Engine:
 
     def set_friction_all(self, mu: float):
         self.set_option(OPT_FRICTION_ALL, mu)
+
+    def set_contacts(self, on: bool):
+        """walker2d.py:38-41 reads world.collision_result.contacts after a step; the fused step records them
+        only when asked (356 B per world per step).  Engine.substep() always records."""
+        self.set_option(OPT_CONTACTS, 1 if on else 0)
 
     def set_max_episode_steps(self, n: int):
         self.set_option(OPT_MAX_EPISODE_STEPS, n)

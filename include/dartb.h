@@ -106,7 +106,11 @@ enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
        DARTB_OPT_FRICTION_ALL = 3,/* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */
        DARTB_OPT_MAX_EPISODE_STEPS = 4,/* TimeLimit (gym/wrappers/time_limit.py:14-21); 0 = off */
        DARTB_OPT_KERNEL_VARIANT = 5, /* -1 = auto, 0 = unrolled per-topology kernel (one world per thread), 1 = loop / topology-generic kernel, 2 = lane-cooperative kernel (8/16 lanes per world) */
-       DARTB_OPT_WORLDS_PER_WARP = 6 /* launch shape of dartb_step: worlds per warp, 0 = auto; results do not depend on it */ };
+       DARTB_OPT_WORLDS_PER_WARP = 6,/* launch shape of dartb_step: worlds per warp, 0 = auto; results do not depend on it */
+       DARTB_OPT_CONTACTS = 7      /* 1 = dartb_step records world.collision_result.contacts of its last sub-step for
+                                      dartb_get_contacts (walker2d.py:38-41); default 0: the record is 356 B per world
+                                      per step, more than the rest of the step's HBM traffic.  dartb_substep (the
+                                      literal World.step()) always records. */ };
 
 typedef struct dartb_engine* dartb_handle_t;
 
@@ -152,8 +156,8 @@ int dartb_step_host(dartb_handle_t h, const float* h_action, float* h_obs, float
 /* The same step with the reference's vectorised RETURN TYPES (gym/vector/sync_vector_env.py:44-47,73-84):
  * obs_out float32 [n, n_obs] (a fresh copy: VectorEnv(copy=True)), reward_out float64 [n], done_out bool [n]
  * (1 byte each), truncated_out bool [n] or NULL (TimeLimit.truncated, gym/wrappers/time_limit.py:14-21).
- * Any host memory (pageable is fine): the kernel writes into the engine's page-locked staging block and
- * the conversion happens in one pass after the sync. */
+ * Page-locked output arrays are written by the step kernel itself in these types over PCIe (one launch, one
+ * sync, no conversion pass); pageable ones are filled from the engine's page-locked staging block after the sync. */
 int dartb_step_host_gym(dartb_handle_t h, const float* h_action, float* obs_out, double* reward_out,
                         uint8_t* done_out, uint8_t* truncated_out, int32_t auto_reset, void* stream);
 

@@ -301,7 +301,7 @@ def test_gym_surface_single_env_types(models):
 
 
 def test_contacts_readback_walker(models):
-    env = _make("DartWalker2d-v1", num_envs=256, output="torch", seed=3)
+    env = _make("DartWalker2d-v1", num_envs=256, output="torch", seed=3, contacts=True)
     env.reset()
     for _ in range(80):
         env.step(torch.zeros((256, 6), device="cuda"))

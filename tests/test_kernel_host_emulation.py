@@ -95,7 +95,7 @@ def _random_contact_lcp(rng, nc, nl, mu=1.0, rank_def=False):
     return A, b, lo, hi, fi
 
 
-@pytest.mark.parametrize("mode,maxn", [(0, 20), (4, 4), (5, 6), (1, 8), (2, 20), (3, 20), (6, 4), (7, 6), (8, 8)])
+@pytest.mark.parametrize("mode,maxn", [(0, 20), (4, 4), (5, 6), (1, 8), (2, 20), (3, 20), (6, 4), (7, 6), (8, 8), (9, 20)])
 def test_kernel_lcp_solvers_equal_oracle_dantzig(mode, maxn):
     """Every LCP code path of the kernel (register block pivoting <4>/<6>/<8>, thread-local block
     pivoting, Dantzig, and the dispatch) returns the oracle's Dantzig solution: the two-stage

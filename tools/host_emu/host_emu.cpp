@@ -141,7 +141,7 @@ extern "C" float emu_reset_uniform(uint64_t seed, int64_t world, uint32_t episod
 }
 
 // standalone LCP entry for tests: mode 0 = lcp_exact dispatch, 1 = lcp_small<8>, 2 = lcp_bpp_local,
-// 3 = lcp_dantzig, 4 = lcp_small<4>, 5 = lcp_small<6>, 6/7/8 = lcp_ppt<4/6/8>.  Returns 0 ok, 1 solver reported failure.
+// 3 = lcp_dantzig, 4 = lcp_small<4>, 5 = lcp_small<6>, 6/7/8 = lcp_ppt<4/6/8>, 9 = lcp_ppt_loop.  Returns 0 ok, 1 solver reported failure.
 template <typename R>
 static int run_lcp(int n, const double* A, const double* b, const double* lo, const double* hi, const int* fidx, int mode,
                    double* x) {
@@ -162,6 +162,7 @@ static int run_lcp(int n, const double* A, const double* b, const double* lo, co
     else if (mode == 6) ok = lcp_ppt<R, 4>(n, a, xx, bb, l, h, fi);
     else if (mode == 7) ok = lcp_ppt<R, 6>(n, a, xx, bb, l, h, fi);
     else if (mode == 8) ok = lcp_ppt<R, 8>(n, a, xx, bb, l, h, fi);
+    else if (mode == 9) ok = lcp_ppt_loop<R, NR>(n, a, xx, bb, l, h, fi);
     for (int i = 0; i < n; i++) x[i] = (double)xx[i];
     return ok ? 0 : 1;
 }
