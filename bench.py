@@ -2,21 +2,32 @@
 """bench.py — env steps/sec of the batched DART stepper (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--env DartHopper-v1] [--worlds 4096] [--allgather] [--lcp exact|pgs]
+                    [--config 2|3|4|5] [--no-extras]
+                    [--env ID --worlds N --lcp exact|pgs --pgs-iters I --allgather]   (custom workload)
 
 One "step" = one env.step() of every world on this rank: action -> frame_skip DART time steps
--> obs / reward / done -> auto-reset.  Workload at N=1: BASELINE configs[1], DartHopper-v1,
-4096 worlds, fp32, frame_skip 4, random actions U(-1,1).  For N>1 launch with torchrun (one rank
-per GPU); worlds are sharded `--worlds` per GPU (weak scaling), no data-path collective unless
---allgather (BASELINE config 4's optional obs all-gather).
+-> obs / reward / done -> auto-reset.  The line's workload is BASELINE configs[1] (`--config 2`:
+DartHopper-v1, 4096 worlds per GPU, fp32, frame_skip 4, random actions U(-1,1)) unless another
+config is asked for; the other GPU configs of BASELINE.json are measured in the same run, shorter,
+and reported under "configs" (per-GPU shard sizes; the NCCL obs all-gather of config 4 INSIDE the
+timed region when there is more than one rank; the PGS iteration sweep of config 5):
+
+    2  DartHopper-v1       4096 worlds/GPU   exact LCP
+    3  DartWalker2d-v1     16384 worlds      PGS LCP path (30 sweeps), exact LCP beside it
+    4  DartHalfCheetah-v1  16384 worlds/GPU  exact LCP + all_gather_into_tensor(obs) per step
+    5  DartSnake7Link-v1   4096 worlds/GPU   PGS iteration sweep k in {1,2,4,8,16,30,50}
+
+For N>1 launch with torchrun (one rank per GPU); worlds are sharded per GPU (weak scaling), no
+data-path collective except config 4's all-gather.
 
 Timing: W warm-up steps, then K steps; each timed step is bracketed by CUDA events on the
 launching stream and L2 is flushed (a 256 MiB write, untimed) between steps because the whole
-working set (0.2 MB) is far smaller than L2; max over ranks.  `value` is device-resident
-throughput; `e2e` goes through the public host API (DartEnv.step with numpy arrays: pinned
-H2D of the actions, kernel, D2H of obs/reward/done) and is the headline against
-`--impl reference`, which times the CPU restatement of the reference path (oracle/, "port":
-pydart2/DART are not installable here) on all host threads.
+working set is far smaller than L2; max over ranks.  `value` is device-resident throughput;
+`e2e` goes through the public host API (DartEnv.step with numpy arrays: the kernel reads the
+actions from and writes obs / float64 rewards / bool dones to page-locked host memory, one launch
++ one sync per step) and is the headline against `--impl reference`, which times the CPU
+restatement of the reference path (oracle/, "port": pydart2/DART are not installable here) on all
+host threads for at least 8 s of CPU work regardless of --steps.
 """
 import argparse
 import json
@@ -32,9 +43,14 @@ os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 
 import numpy as np  # noqa: E402
 
-METRIC = "env steps/sec (batched worlds) DartHopper-v1"
 UNIT = "env-steps/s"
-ALGO_BYTES = {6: 157, 9: 241}  # 4*(2nd + nact + 2nd + nobs + 1) + 1 per env step
+CONFIGS = {
+    2: dict(env="DartHopper-v1", worlds=4096, lcp="exact", pgs_iters=30, allgather=False),
+    3: dict(env="DartWalker2d-v1", worlds=16384, lcp="pgs", pgs_iters=30, allgather=False),
+    4: dict(env="DartHalfCheetah-v1", worlds=16384, lcp="exact", pgs_iters=30, allgather=True),
+    5: dict(env="DartSnake7Link-v1", worlds=4096, lcp="pgs", pgs_iters=30, allgather=False),
+}
+PGS_SWEEP = (1, 2, 4, 8, 16, 30, 50)
 
 
 def build_model(env_id):
@@ -51,6 +67,17 @@ def build_model(env_id):
 
 def metric_name(env_id):
     return "env steps/sec (batched worlds) %s" % env_id
+
+
+def workload_string(env_id, worlds, frame_skip, lcp, pgs_iters):
+    """the SAME string in both arms (the driver compares them)"""
+    return "%s, %d worlds/GPU, fp32 engine, frame_skip %d, random actions U(-1,1), auto-reset, lcp=%s" % (
+        env_id, worlds, frame_skip, lcp if lcp == "exact" else "pgs(%d)" % pgs_iters)
+
+
+def algo_bytes(nd, nact, nobs):
+    """4*(2nd [q,dq in] + nact + 2nd [q,dq out] + nobs + 1 [reward]) + 1 [done] per env step"""
+    return 4 * (4 * nd + nact + nobs + 1) + 1
 
 
 def host_threads():
@@ -107,56 +134,153 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_arm(env_id, worlds, steps, warmup, threads, budget_s=60.0):
-    """The CPU restatement of the reference path (oracle 'port'), all host threads, auto-reset,
-    same random-action distribution.  `steps=None`: choose the step count for about `budget_s`
-    seconds of CPU work over all `worlds`; otherwise keep `steps` and bound the per-step sample of
-    worlds so the run ends in about `budget_s`."""
+def cpu_arm(env_id, worlds, threads, budget_s, block_steps=25):
+    """The CPU restatement of the reference path (oracle 'port'): all `worlds` worlds of the workload, all host
+    threads, auto-reset, the same random-action distribution; blocks of `block_steps` env steps are repeated
+    until about `budget_s` seconds of CPU work have been timed (so the figure does not depend on --steps)."""
     from oracle import oracle as orc
     m, spec = build_model(env_id)
-    cal_w = max(threads * 8, 64)
-    orc.cpu_bench(m, spec.task, cal_w, 5, threads, seed=1)  # page in
-    t0 = time.perf_counter()
-    orc.cpu_bench(m, spec.task, cal_w, 40, threads, seed=1)
-    rate = cal_w * 40 / max(time.perf_counter() - t0, 1e-6)
-    if steps is None:
-        # run chunks of 25 steps over all worlds until about budget_s of CPU work has been timed
-        sample, steps, wall = worlds, 0, 0.0
-        while wall < budget_s and steps < 100000:
-            t0 = time.perf_counter()
-            orc.cpu_bench(m, spec.task, sample, 25, threads, seed=3 + steps)
-            wall += time.perf_counter() - t0
-            steps += 25
-    else:
-        sample = int(min(worlds, max(threads, rate * budget_s / max(steps + warmup, 1))))
-        if warmup > 0:
-            orc.cpu_bench(m, spec.task, sample, warmup, threads, seed=2)
+    orc.cpu_bench(m, spec.task, max(threads * 8, 64), 5, threads, seed=1)  # page in, spin the threads up
+    steps, wall = 0, 0.0
+    while wall < budget_s and steps < 1000000:
         t0 = time.perf_counter()
-        orc.cpu_bench(m, spec.task, sample, steps, threads, seed=3)
-        wall = time.perf_counter() - t0
-    return {"value": sample * steps / wall, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d of %d worlds per step x %d steps (%.1f s of CPU work), fp64 scalar C restatement of "
-                      "pydart2 World.step + task layer, %d pthreads" % (sample, worlds, steps, wall, threads)}, wall, steps
+        orc.cpu_bench(m, spec.task, worlds, block_steps, threads, seed=3 + steps)
+        wall += time.perf_counter() - t0
+        steps += block_steps
+    return {"value": worlds * steps / wall, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d worlds x %d env steps (%.1f s of CPU work, blocks of %d steps), fp64 scalar C restatement of "
+                      "pydart2 World.step (Dantzig LCP) + task layer, %d pthreads" % (worlds, steps, wall, block_steps, threads)}, wall, steps
 
 
-def run_reference(args, rank, world_size):
+def run_reference(args, cfg, rank):
     if rank != 0:
         return
     threads = host_threads()
-    cb, wall, _ = cpu_arm(args.env, args.worlds, args.steps, args.warmup, threads)
-    line = {"impl": "reference", "metric": metric_name(args.env), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+    m, spec = build_model(cfg["env"])
+    cb, wall, steps = cpu_arm(cfg["env"], cfg["worlds"], threads, budget_s=10.0, block_steps=max(1, min(args.steps, 25)))
+    extras = {}
+    if not args.no_extras:
+        for cid, c in CONFIGS.items():
+            if c["env"] == cfg["env"]:
+                continue
+            e, _, _ = cpu_arm(c["env"], min(c["worlds"], 4096), threads, budget_s=4.0)
+            extras[str(cid)] = {"env": c["env"], "value": e["value"], "unit": UNIT, "cpu_baseline": e}
+    line = {"impl": "reference", "metric": metric_name(cfg["env"]), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s, %d worlds, frame_skip %d, random actions U(-1,1), auto-reset; CPU arm: %s"
-                       % (args.env, args.worlds, 4, cb["sample"])},
+            "config": {"workload": workload_string(cfg["env"], cfg["worlds"], spec.task.frame_skip, cfg["lcp"], cfg["pgs_iters"]),
+                       "timed": "%d env steps of all %d worlds = %.1f s on %d host threads (--steps only sets the block size)"
+                                % (steps, cfg["worlds"], wall, threads)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "configs": extras}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------ GPU arm
-def run_ours(args, rank, local_rank, world_size):
+def load_profile():
+    for name in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))), "profiles/" + name
+        except Exception:
+            continue
+    return {}, None
+
+
+class Runner:
+    """one workload on this rank: engine, action pool, timed loops"""
+
+    def __init__(self, torch, dist, cfg, rank, local_rank, world_size, seed):
+        from dart_env_b200.envs import make
+        self.torch, self.dist, self.cfg, self.rank, self.world_size = torch, dist, cfg, rank, world_size
+        self.dev = torch.device("cuda", local_rank)
+        n = self.n = cfg["worlds"]
+        self.m, self.spec = build_model(cfg["env"])
+        self.nact, self.nobs, self.nd = self.spec.task.n_act, self.spec.task.n_obs, self.m.n_dofs
+        self.env = make(cfg["env"], num_envs=n, output="torch", device=local_rank, seed=seed, world_offset=rank * n, batched=True)
+        self.eng = self.env.engine
+        if cfg["lcp"] == "pgs":
+            self.eng.set_lcp(1, cfg["pgs_iters"])
+        gen = torch.Generator(device=self.dev)
+        gen.manual_seed(1234 + rank)
+        # actions: a pool of 64 pre-generated U(-1,1) batches cycled through (BASELINE.md regenerates them on the device
+        # every step; a torch RNG kernel inside the timed region would not be this repo's kernel)
+        self.pool = [(torch.rand((n, self.nact), generator=gen, device=self.dev) * 2 - 1).contiguous() for _ in range(64)]
+        self.gather = None
+        if cfg["allgather"] and world_size > 1:
+            self.gather = torch.empty((world_size * n, self.nobs), dtype=torch.float32, device=self.dev)
+        self.env.reset()
+        self.i = 0
+
+    def one_step(self):
+        env = self.env
+        self.eng.step(self.pool[self.i % 64], env._obs, env._rew, env._done, True)
+        if self.gather is not None:
+            self.dist.all_gather_into_tensor(self.gather, env._obs)
+        self.i += 1
+
+    def warm(self, W):
+        for _ in range(W):
+            self.one_step()
+        self.torch.cuda.synchronize()
+
+    def timed_flushed(self, K, flush):
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = self.eng.launch_count
+        for i in range(K):
+            flush.fill_(float(i & 1))
+            ev[i][0].record()
+            self.one_step()
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in ev)), self.eng.launch_count - l0
+
+    def timed_warm(self, K):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            self.one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def done_fraction(self):
+        return float((self.env._done != 0).float().mean().item())
+
+    def close(self):
+        self.env.close()
+
+
+def reduce_max(torch, dist, dev, world_size, vals):
+    if world_size == 1:
+        return list(vals)
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def roofline(r, kern_ms, peak, peak_src, prof, prof_src):
+    bpl = algo_bytes(r.nd, r.nact, r.nobs) * r.n
+    achieved = bpl / (kern_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "kernel": r.eng.kernel_name, "algorithmic_bytes_per_env_step": bpl // r.n,
+            "note": "fused per-world stepper: only the API-boundary I/O crosses HBM, so the HBM fraction is small by "
+                    "construction; the kernel is bound by dependent-issue latency / instruction issue (issue_active_pct, "
+                    "avg_active_lanes from the committed ncu capture of this kernel)"}
+    key = "%s/%d/%s" % (r.cfg["env"], r.n, "coop" if "coop:" in r.eng.kernel_name else "static")
+    p = prof.get(key) or prof.get(r.cfg["env"] if "coop:" in r.eng.kernel_name else r.cfg["env"] + "/static")
+    if isinstance(p, dict):
+        roof["traffic"] = p.get("dram_bytes_per_launch")
+        for k in ("fp32", "fp64", "issue_active_pct", "warps_active_pct", "avg_active_lanes", "stall_pct", "duration_us"):
+            if k in p:
+                roof[k if k != "duration_us" else "ncu_duration_us"] = p[k]
+        roof["profile"] = "%s[%s]" % (prof_src, key)
+    return roof
+
+
+def run_ours(args, cfg, rank, local_rank, world_size):
     import torch
     import torch.distributed as dist
 
@@ -168,143 +292,135 @@ def run_ours(args, rank, local_rank, world_size):
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.worlds
-    m, spec = build_model(args.env)
-    nact, nobs, nd = spec.task.n_act, spec.task.n_obs, m.n_dofs
     K, W = args.steps, max(args.warmup, 3)
-
-    env = make(args.env, num_envs=n, output="torch", device=local_rank, seed=args.seed, world_offset=rank * n,
-               batched=True)
-    eng = env.engine
-    if args.lcp == "pgs":
-        eng.set_lcp(1, args.pgs_iters)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    pool = [(torch.rand((n, nact), generator=gen, device=dev) * 2 - 1).contiguous() for _ in range(64)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    gather = torch.empty((world_size * n, nobs), dtype=torch.float32, device=dev) if (args.allgather and world_size > 1) else None
-    obs, rew, done = env._obs, env._rew, env._done
-    env.reset()
+    prof, prof_src = load_profile()
+    peaks, peak_src = None, "fallback (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
 
-    def one_step(i):
-        eng.step(pool[i % 64], obs, rew, done, True)
-        if gather is not None:
-            dist.all_gather_into_tensor(gather, obs)
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
+    # ---- headline workload
+    r = Runner(torch, dist, cfg, rank, local_rank, world_size, args.seed)
+    n, nact, nobs = r.n, r.nact, r.nobs
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(W):
-        one_step(i)
-    torch.cuda.synchronize()
+    r.warm(W)
     t_w = time.perf_counter()
     while not sampler.lines and sampler.proc is not None and time.perf_counter() - t_w < 2.0:
-        one_step(0)   # keep the GPU under load until nvidia-smi delivers its first sample
+        r.one_step()   # keep the GPU under load until nvidia-smi delivers its first sample
         torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-
-    # ---- device-resident throughput: per-step CUDA events, L2 flushed (untimed) between steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    l0 = eng.launch_count
+    barrier()
     t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(float(i & 1))
-        ev[i][0].record()
-        one_step(W + i)
-        ev[i][1].record()
-    torch.cuda.synchronize()
+    dev_ms, launches = r.timed_flushed(K, flush)
     t_wall = time.perf_counter() - t_wall0
-    launches = eng.launch_count - l0
-    per = np.array([a.elapsed_time(b) for a, b in ev])  # ms
-    dev_ms = float(per.sum())
-    # warm-L2, back-to-back (the steady state of a training loop), one event pair around K steps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        one_step(W + K + i)
-    e1.record()
-    torch.cuda.synchronize()
-    warm_ms = e0.elapsed_time(e1)
-    done_frac = float((done != 0).float().mean().item())
+    barrier()
+    warm_ms = r.timed_warm(K)
+    done_frac = r.done_fraction()
 
-    # ---- end to end through the public host API (numpy in / numpy out, pinned staging)
-    henv = make(args.env, num_envs=n, output="numpy", device=local_rank, seed=args.seed, world_offset=rank * n, batched=True)
+    # ---- end to end through the public host API (numpy in / numpy out, page-locked output slots)
+    henv = make(cfg["env"], num_envs=n, output="numpy", device=local_rank, seed=args.seed, world_offset=rank * n, batched=True)
+    if cfg["lcp"] == "pgs":
+        henv.engine.set_lcp(1, cfg["pgs_iters"])
     henv.reset()
     rng = np.random.RandomState(99 + rank)
     hpool = [rng.uniform(-1, 1, (n, nact)).astype(np.float32) for _ in range(16)]
-    Ke = K
     for i in range(W):
         henv.step(hpool[i % 16])
-    torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
+    barrier()
     e2e_s = 0.0
-    for i in range(Ke):
+    for i in range(K):
         flush.fill_(float(i & 1))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        o, r, d, _ = henv.step(hpool[i % 16])
+        o, rw, d, _ = henv.step(hpool[i % 16])
         e2e_s += time.perf_counter() - t0
-    h2d, d2h = n * nact * 4, n * nobs * 4 + n * 4 + n
+    assert o.dtype == np.float32 and rw.dtype == np.float64 and d.dtype == np.bool_
+    h2d, d2h = n * nact * 4, n * nobs * 4 + n * 8 + n
+    henv.close()
     clocks = sampler.stop()   # sampled over all three timed regions (flushed, warm, end-to-end)
-
-    if world_size > 1:
-        t = torch.tensor([dev_ms, warm_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, warm_ms, e2e_s = [float(x) for x in t.tolist()]
+    dev_ms, warm_ms, e2e_s = reduce_max(torch, dist, dev, world_size, (dev_ms, warm_ms, e2e_s))
     total_worlds = n * world_size
-    value = total_worlds * K / (dev_ms * 1e-3)
+    roof = roofline(r, dev_ms / K, peak, peak_src, prof, prof_src) if rank == 0 else None
+    kernel_name = r.eng.kernel_name
+    r.close()
+
+    # ---- the other GPU configs of BASELINE.json, shorter, in the same run
+    extras = {}
+    if not args.no_extras:
+        Ke, We = max(20, min(K, 200)), max(3, min(W, 20))
+        for cid, c in CONFIGS.items():
+            if c["env"] == cfg["env"] and c["worlds"] == cfg["worlds"]:
+                continue
+            variants = [c]
+            if cid == 3:
+                variants = [c, dict(c, lcp="exact")]
+            out = {"env": c["env"], "worlds_per_gpu": c["worlds"], "runs": []}
+            for v in variants:
+                x = Runner(torch, dist, v, rank, local_rank, world_size, args.seed)
+                x.warm(We)
+                barrier()
+                ms, nl = x.timed_flushed(Ke, flush)
+                barrier()
+                wm = x.timed_warm(Ke)
+                ms, wm = reduce_max(torch, dist, dev, world_size, (ms, wm))
+                run = {"lcp": v["lcp"] if v["lcp"] == "exact" else "pgs(%d)" % v["pgs_iters"],
+                       "value": x.n * world_size * Ke / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / Ke,
+                       "value_l2_warm": x.n * world_size * Ke / (wm * 1e-3), "ms_per_step_l2_warm": wm / Ke, "steps": Ke,
+                       "gpu_launches": int(nl), "done_fraction": x.done_fraction(),
+                       "parallelism": "worlds sharded x%d%s" % (world_size, ", all_gather_into_tensor(obs [%d,%d] fp32) inside every timed step"
+                                                                % (x.n * world_size, x.nobs) if x.gather is not None else
+                                                                (", obs all-gather is a no-op on one rank" if v["allgather"] else ", no collective"))}
+                if rank == 0:
+                    run["roofline"] = roofline(x, ms / Ke, peak, peak_src, prof, prof_src)
+                out["runs"].append(run)
+                if cid == 5 and v is variants[-1]:
+                    sweep = []
+                    for k in PGS_SWEEP:
+                        x.eng.set_lcp(1, k)
+                        x.warm(5)
+                        barrier()
+                        wk = reduce_max(torch, dist, dev, world_size, (x.timed_warm(max(20, Ke // 2)),))[0] / max(20, Ke // 2)
+                        sweep.append({"pgs_iters": k, "us_per_step_l2_warm": 1e3 * wk, "value": x.n * world_size / (wk * 1e-3)})
+                    out["pgs_sweep"] = sweep
+                x.close()
+            extras[str(cid)] = out
+
     line = None
     if rank == 0:
-        peaks, peak_src = None, "fallback"
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak_src = "measured"
-        except Exception:
-            pass
-        peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
-        bytes_per_launch = ALGO_BYTES.get(nd, 4 * (4 * nd + nact + nobs + 1) + 1) * n
-        kern_ms = dev_ms / K
-        achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-            traffic = prof.get(args.env, {}).get("dram_bytes_per_launch")
-        except Exception:
-            prof = {}
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": eng.kernel_name,
-                "note": "fused per-world stepper: only the API-boundary I/O (%d B/env-step) crosses HBM, so the HBM "
-                        "fraction is small by construction; the kernel is bound by dependent-issue latency (see profiles/)"
-                        % (bytes_per_launch // n)}
-        # counted arithmetic of the captured kernel form (profiles/): key "<env>" = lane-cooperative, "<env>/static" = per-thread
-        pkey = args.env if "coop:" in eng.kernel_name or (args.env + "/static") not in prof else args.env + "/static"
-        if isinstance(prof, dict) and pkey in prof:
-            roof["traffic"] = prof[pkey].get("dram_bytes_per_launch", traffic)
-            for k in ("fp32", "fp64", "issue_active_pct", "warps_active_pct", "stall_pct"):
-                if k in prof[pkey]:
-                    roof[k] = prof[pkey][k]
-            roof["profile"] = "profiles/r1_ncu_summary.json[%s]" % pkey
-        cb = None
-        if world_size >= 1:
-            cb, _, _ = cpu_arm(args.env, n, None, 5, host_threads(), budget_s=12.0)
-        line = {"metric": metric_name(args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
-                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": "%s, %d worlds/GPU, fp32, frame_skip %d, random actions U(-1,1), auto-reset, lcp=%s"
-                                       % (args.env, n, spec.task.frame_skip, args.lcp),
-                           "worlds_per_gpu": n, "parallelism": "worlds sharded x%d, no data-path collective%s"
-                                                               % (world_size, " + obs all_gather" if gather is not None else ""),
-                           "l2": "flushed between timed steps (256 MiB write, untimed); working set 0.2 MB << L2",
+        cb, _, _ = cpu_arm(cfg["env"], n, host_threads(), budget_s=10.0)
+        if not args.no_extras:
+            for cid, c in CONFIGS.items():
+                if str(cid) in extras:
+                    extras[str(cid)]["cpu_baseline"] = cpu_arm(c["env"], min(c["worlds"], 4096), host_threads(), budget_s=4.0)[0]
+        line = {"metric": metric_name(cfg["env"]), "value": total_worlds * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world_size,
+                "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_string(cfg["env"], n, r.spec.task.frame_skip, cfg["lcp"], cfg["pgs_iters"]),
+                           "worlds_per_gpu": n,
+                           "parallelism": "worlds sharded x%d, %s" % (world_size, "obs all_gather_into_tensor inside the timed step"
+                                                                     if (cfg["allgather"] and world_size > 1) else "no data-path collective"),
+                           "actions": "pool of 64 pre-generated U(-1,1) batches per rank, cycled (not regenerated per step)",
+                           "l2": "flushed between timed steps (256 MiB write, untimed); working set %.1f MB << L2"
+                                 % (algo_bytes(r.nd, nact, nobs) * n / 1e6),
                            "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks"},
                 "value_l2_warm": total_worlds * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
-                "wall_s_timed_loop": t_wall, "done_fraction": done_frac,
-                "e2e": {"value": total_worlds * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_s / Ke, "api": "DartEnv.step(numpy) -> numpy (pinned H2D, kernel, D2H, sync)"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks}
+                "wall_s_timed_loop": t_wall, "done_fraction": done_frac, "kernel": kernel_name,
+                "e2e": {"value": total_worlds * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * e2e_s / K,
+                        "api": "DartEnv.step(numpy float32 [N,nact]) -> (float32 obs, float64 rewards, bool dones): one launch + one "
+                               "sync; the kernel reads / writes page-locked host memory itself"},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "configs": extras}
         print(json.dumps(line), flush=True)
-    env.close(); henv.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -317,23 +433,34 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--env", default="DartHopper-v1")
-    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config the line is quoted on")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs (reported under 'configs')")
+    ap.add_argument("--env", default=None, help="custom workload: env id (overrides --config)")
+    ap.add_argument("--worlds", type=int, default=None, help="worlds per GPU")
     ap.add_argument("--allgather", action="store_true")
-    ap.add_argument("--lcp", default="exact", choices=["exact", "pgs"])
-    ap.add_argument("--pgs-iters", type=int, default=30)
+    ap.add_argument("--lcp", default=None, choices=["exact", "pgs"])
+    ap.add_argument("--pgs-iters", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.env:
+        cfg.update(env=args.env, lcp="exact", allgather=False, worlds=4096)
+        args.no_extras = True
+    for k, v in (("worlds", args.worlds), ("lcp", args.lcp), ("pgs_iters", args.pgs_iters)):
+        if v is not None:
+            cfg[k] = v
+    if args.allgather:
+        cfg["allgather"] = True
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world_size)
+        run_reference(args, cfg, rank)
         return
     if world_size == 1 and args.gpus > 1:
         raise SystemExit("bench.py: --gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d ...)"
                          % (args.gpus, args.gpus))
-    run_ours(args, rank, local_rank, world_size)
+    run_ours(args, cfg, rank, local_rank, world_size)
 
 
 if __name__ == "__main__":

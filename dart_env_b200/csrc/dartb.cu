@@ -71,7 +71,7 @@ struct dartb_engine {
     PTask<float> tf; PTask<double> td;
     dartb_model_t model; dartb_task_t task;   // kept so friction/options can re-lower
     void* q = nullptr; void* dq = nullptr;
-    void* scratch = nullptr;                  // [n * max(nd, nbd*3)] of Real for tau / fext conversion
+    void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
     uint64_t* hint = nullptr;                 // LCP warm-start sets, see planar_kernels.cuh::substep
     int32_t* ccount = nullptr; int32_t* cbody = nullptr; float* cdata = nullptr;
@@ -316,7 +316,7 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
     if (lower_into(e)) { delete e; return 1; }
     DeviceGuard g(device);
     const size_t rs = f64 ? 8 : 4;
-    const size_t sc = (size_t)n * (size_t)std::max(e->nd, e->n_orig_bodies * 3);
+    const size_t sc = (size_t)n * (size_t)(e->nd + e->n_orig_bodies * 3);   // tau region, then fext region
     cudaError_t err = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) err = cudaMemset(*p, 0, bytes); } };
     A(&e->q, rs * n * e->nd); A(&e->dq, rs * n * e->nd); A(&e->scratch, rs * sc);
@@ -433,6 +433,12 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             e->max_episode_steps = (int)value; return 0;
     }
     return fail("unknown option key");
+}
+
+int dartb_seed(dartb_handle_t e, uint64_t seed) {
+    if (!e) return fail("null handle");
+    e->seed = seed;   // a kernel argument: takes effect with the next launch, no synchronisation
+    return 0;
 }
 
 int dartb_reset(dartb_handle_t e, const uint8_t* d_mask, float* d_obs, void* stream) {
@@ -617,9 +623,9 @@ int dartb_substep(dartb_handle_t e, const float* d_tau, const float* d_fext, voi
     // fp64 engine fed fp32 inputs: widen through the scratch buffer
     double* sc = (double*)e->scratch;
     const double* tau = nullptr; const double* fx = nullptr;
-    if (d_tau && d_fext) return fail("fp64 engine: pass tau and fext through dartb_substep_f64");
+    double* sf = sc + (size_t)e->n * e->nd;
     if (d_tau) { size_t k = (size_t)e->n * e->nd; k_convert<float, double><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_tau, sc); tau = sc; e->launches++; }
-    if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<float, double><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sc); fx = sc; e->launches++; }
+    if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<float, double><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sf); fx = sf; e->launches++; }
     return launch_substep<double>(e, tau, fx, st);
 }
 int dartb_substep_f64(dartb_handle_t e, const double* d_tau, const double* d_fext, void* stream) {
@@ -627,11 +633,11 @@ int dartb_substep_f64(dartb_handle_t e, const double* d_tau, const double* d_fex
     DeviceGuard g(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (e->f64) return launch_substep<double>(e, d_tau, d_fext, st);
-    if (d_tau && d_fext) return fail("fp32 engine: pass tau and fext through dartb_substep");
     float* sc = (float*)e->scratch;
+    float* sf = sc + (size_t)e->n * e->nd;
     const float* tau = nullptr; const float* fx = nullptr;
     if (d_tau) { size_t k = (size_t)e->n * e->nd; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_tau, sc); tau = sc; e->launches++; }
-    if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sc); fx = sc; e->launches++; }
+    if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sf); fx = sf; e->launches++; }
     return launch_substep<float>(e, tau, fx, st);
 }
 

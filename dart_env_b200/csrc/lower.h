@@ -182,6 +182,13 @@ static std::string lower_model(const dartb_model_t& dm, const dartb_task_t& dt_,
         m.ox[gi] = dot(e1, o);
         m.oy[gi] = dot(e2, o);
         V3 ez = rot(Tw[r], v3(0, 0, 1));
+        if (dt_.fluid_force) {
+            // the fluid force mixes the BODY-frame COM velocity with the WORLD-frame normal (snake_7link.py:37-45); the
+            // planar kernels restate that for body frames that coincide with the world axes at the zero pose
+            for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++)
+                if (std::fabs(Tw[r].R[3 * a + c] - (a == c ? 1.0 : 0.0)) > 1e-9)
+                    return "fluid force needs body frames aligned with the world axes at the zero pose";
+        }
         m.fnx[gi] = dot(e1, ez);
         m.fny[gi] = dot(e2, ez);
         std::snprintf(buf, sizeof buf, "%c%d,", b.joint_type == DARTB_JOINT_REVOLUTE ? 'R' : 'P', pg);

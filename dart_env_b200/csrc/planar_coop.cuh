@@ -788,7 +788,8 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
     if constexpr (FLUID) {
         // snake_7link.py:35-47: bn.com_spatial_velocity(), norm_dir = R*ez, add_ext_force at the body origin
         const R nx = cs * c.fnx - sn * c.fny, ny = sn * c.fnx + cs * c.fny;
-        const R vcx = vx - wz * dcy, vcy = vy + wz * dcx;
+        const R vwx = vx - wz * dcy, vwy = vy + wz * dcx;
+        const R vcx = cs * vwx + sn * vwy, vcy = cs * vwy - sn * vwx;   // body coordinates (see planar_kernels.cuh::substep)
         const R crx = -wz * ny, cry = wz * nx;
         const R dp = (vcx + crx * fluid_offset) * nx + (vcy + cry * fluid_offset) * ny;
         const R dn = (vcx - crx * fluid_offset) * nx + (vcy - cry * fluid_offset) * ny;

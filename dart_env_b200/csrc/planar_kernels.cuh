@@ -1126,8 +1126,12 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
             if constexpr (FLUID) {
                 // bn.com_spatial_velocity(), norm_dir = R*ez, add_ext_force at the body origin
                 const R nx = cs[i] * M.fnx[i] - sn[i] * M.fny[i], ny = sn[i] * M.fnx[i] + cs[i] * M.fny[i];
-                const R vcx = vx[i] - wz[i] * dy, vcy = vy[i] + wz[i] * dx;  // COM velocity (origin = DART origin here)
-                const R crx = -wz[i] * ny, cry = wz[i] * nx;                 // omega x n
+                // COM velocity in BODY coordinates: pydart2's no-argument com_spatial_velocity() is DART's
+                // BodyNode::getCOMSpatialVelocity(), expressed in the body frame; the reference dots it with the
+                // WORLD-frame norm_dir component by component (snake_7link.py:37-45), and so do we
+                const R vwx = vx[i] - wz[i] * dy, vwy = vy[i] + wz[i] * dx;  // COM velocity, world axes
+                const R vcx = cs[i] * vwx + sn[i] * vwy, vcy = cs[i] * vwy - sn[i] * vwx;
+                const R crx = -wz[i] * ny, cry = wz[i] * nx;                 // omega x n (omega is the same in both frames)
                 const R dp = (vcx + crx * fluid_offset) * nx + (vcy + cry * fluid_offset) * ny;
                 const R dn = (vcx - crx * fluid_offset) * nx + (vcy - cry * fluid_offset) * ny;
                 R ffx = 0, ffy = 0;

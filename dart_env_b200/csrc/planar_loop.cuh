@@ -101,7 +101,8 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
         if (FEXT) { pt -= eft[i]; pfx -= efx[i]; pfy -= efy[i]; }
         if (FLUID) {
             const R nx = cs[i] * M.fnx[i] - sn[i] * M.fny[i], ny = sn[i] * M.fnx[i] + cs[i] * M.fny[i];
-            const R vcx = vx[i] - wz[i] * dy, vcy = vy[i] + wz[i] * dx;
+            const R vwx = vx[i] - wz[i] * dy, vwy = vy[i] + wz[i] * dx;
+            const R vcx = cs[i] * vwx + sn[i] * vwy, vcy = cs[i] * vwy - sn[i] * vwx;   // body coordinates (see planar_kernels.cuh)
             const R crx = -wz[i] * ny, cry = wz[i] * nx;
             const R dp = (vcx + crx * fluid_offset) * nx + (vcy + cry * fluid_offset) * ny;
             const R dn = (vcx - crx * fluid_offset) * nx + (vcy - cry * fluid_offset) * ny;

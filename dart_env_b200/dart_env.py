@@ -198,7 +198,10 @@ class DartEnv:
             seed = int.from_bytes(os.urandom(4), "little")
         self._seed_value = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.np_random = np.random.RandomState(self._seed_value & 0xFFFFFFFF)
-        self._build_engine()
+        if self.engine is None:
+            self._build_engine()
+        else:   # like the reference, seeding does not touch the physics state
+            capi.check(self.engine.L.dartb_seed(self.engine.h, self._seed_value))
         return [self._seed_value]
 
     def close(self):
@@ -289,6 +292,9 @@ class DartEnv:
     def step(self, a):
         if not self.fused:
             raise NotImplementedError("host-side task classes implement step()")
+        if self.add_perturbation:
+            raise NotImplementedError("add_perturbation (dart_env.py:159-172) is applied by do_simulation(); the fused "
+                                      "step() of this env does not draw perturbation forces")
         if isinstance(a, torch.Tensor) and a.is_cuda:
             act = a.reshape(self.num_envs, self.act_dim).to(torch.float32).contiguous()
             self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)

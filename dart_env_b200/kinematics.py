@@ -60,8 +60,8 @@ def body_com_world(model: Model, q: torch.Tensor) -> torch.Tensor:
 
 
 def body_com_spatial_velocities(model: Model, q: torch.Tensor, dq: torch.Tensor) -> torch.Tensor:
-    """bodynodes[*].com_spatial_velocity() -> [N,nb,6] = [angular; linear velocity of the COM], world axes
-    (pydart2's default frames: relative to and expressed in the world)."""
+    """bodynodes[*].com_spatial_velocity() -> [N,nb,6] = [angular; linear velocity of the COM] relative to the world,
+    expressed in BODY coordinates (pydart2's no-argument call is DART's BodyNode::getCOMSpatialVelocity())."""
     n, dev, dt = q.shape[0], q.device, torch.float64
     q, dq = q.to(dt), dq.to(dt)
     R, p = body_transforms(model, q)
@@ -89,4 +89,5 @@ def body_com_spatial_velocities(model: Model, q: torch.Tensor, dq: torch.Tensor)
         W.append(w); V.append(v)
     W, V = torch.stack(W, 1), torch.stack(V, 1)
     vc = V + torch.cross(W, com - p, dim=2)
-    return torch.cat([W, vc], dim=2)
+    Rt = R.transpose(-1, -2)
+    return torch.cat([(Rt @ W[..., None]).squeeze(-1), (Rt @ vc[..., None]).squeeze(-1)], dim=2)

@@ -435,14 +435,15 @@ _BUNDLED = os.path.join(os.path.dirname(__file__), "assets")
 
 
 def find_asset(model_path: str) -> str:
-    """Resolve a model path like `dart_env.py:44-52`: absolute paths as-is, otherwise relative
-    to an assets dir ($DART_ENV_ASSETS, then the reference checkout if present)."""
+    """Resolve a model path like `dart_env.py:44-52`: absolute paths as-is, otherwise relative to
+    $DART_ENV_ASSETS (a directory of `.skel` files, e.g. the reference's gym/envs/dart/assets) when it
+    is set, else to the bundled assets.  Nothing else is searched: behaviour does not depend on whether
+    a reference checkout happens to be on the machine."""
     if model_path.startswith("/"):
         return model_path
-    ref = None if os.environ.get("DART_ENV_NO_REFERENCE") else "/root/reference/gym/envs/dart/assets"
-    for base in (os.environ.get("DART_ENV_ASSETS"), ref):
-        if base and os.path.exists(os.path.join(base, model_path)):
-            return os.path.join(base, model_path)
+    base = os.environ.get("DART_ENV_ASSETS")
+    if base and os.path.exists(os.path.join(base, model_path)):
+        return os.path.join(base, model_path)
     return os.path.join(_BUNDLED, model_path)
 
 

@@ -124,6 +124,11 @@ int dartb_destroy(dartb_handle_t h);
 
 int dartb_set_option(dartb_handle_t h, int32_t key, double value);
 
+/* env.seed(s) (dart_env.py:117-119): re-keys the reset-noise generator (Philox4x32-10 keyed by seed, global
+ * world id and episode counter).  Like the reference it touches nothing else: physics state, episode counters
+ * and options stay as they are. */
+int dartb_seed(dartb_handle_t h, uint64_t seed);
+
 /* world.reset() + reset_model(): q0 + U(+-noise), dq0 + U(+-noise), returns obs.
  * d_mask: uint8[n] (NULL = all worlds). d_obs may be NULL.  (dart_world.py:20-22, hopper.py:76-84) */
 int dartb_reset(dartb_handle_t h, const uint8_t* d_mask, float* d_obs, void* stream);

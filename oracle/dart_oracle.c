@@ -912,14 +912,14 @@ void orc_body_com(orc_world_t* w, int body, double out[3]) { /* bodynode.com() w
     xf_point(&w->Tw[body], w->m.bodies[body].com, out);
 }
 void orc_body_com_spatial_velocity(orc_world_t* w, int body, double out[6]) {
-    /* [omega; v_com] in world-aligned axes (pydart2 com_spatial_velocity) */
+    /* [omega; v_com] in BODY coordinates: pydart2's no-argument com_spatial_velocity() is DART's
+     * BodyNode::getCOMSpatialVelocity() = getSpatialVelocity(getLocalCOM()), "expressed in coordinates of this
+     * Frame and relative to the World Frame" [RECALLED: DART 6 BodyNode.hpp / Frame.cpp; not in /root/reference] */
     forward_kinematics(w);
     const double* V = w->V[body];
-    double vc[3], t[3];
+    double t[3];
     v3cross(V, w->m.bodies[body].com, t);
-    for (int k = 0; k < 3; k++) vc[k] = V[3 + k] + t[k];
-    m3v(w->Tw[body].R, V, out);
-    m3v(w->Tw[body].R, vc, out + 3);
+    for (int k = 0; k < 3; k++) { out[k] = V[k]; out[3 + k] = V[3 + k] + t[k]; }
 }
 void orc_add_ext_force(orc_world_t* w, int body, const double f[3]) {
     /* world-frame force applied at the body origin (offset 0): pure linear part in body frame */
@@ -1094,13 +1094,12 @@ static void fluid_forces(orc_env_t* e) {
     forward_kinematics(w);
     for (int i = 0; i < w->nb; i++) {
         double sv[6], nrm[3] = {w->Tw[i].R[2], w->Tw[i].R[5], w->Tw[i].R[8]}; /* R * ez */
-        /* com spatial velocity */
+        /* bn.com_spatial_velocity(): BODY-frame components (see orc_body_com_spatial_velocity); the reference
+         * combines them with the WORLD-frame norm_dir component by component (snake_7link.py:37-45) */
         const double* V = w->V[i];
-        double vc[3], tt[3];
+        double tt[3];
         v3cross(V, w->m.bodies[i].com, tt);
-        for (int k = 0; k < 3; k++) vc[k] = V[3 + k] + tt[k];
-        m3v(w->Tw[i].R, V, sv);
-        m3v(w->Tw[i].R, vc, sv + 3);
+        for (int k = 0; k < 3; k++) { sv[k] = V[k]; sv[3 + k] = V[3 + k] + tt[k]; }
         double cr[3], vp[3], vn[3], f[3] = {0, 0, 0};
         v3cross(sv, nrm, cr);
         for (int k = 0; k < 3; k++) { vp[k] = sv[3 + k] + cr[k] * e->t.fluid_offset; vn[k] = sv[3 + k] - cr[k] * e->t.fluid_offset; }

@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/.."
 sfx=$1; shift
-only=${VARIANT_ONLY:-walker_f,cheetah_f,hopper_f,snake_f}
+only=${VARIANT_ONLY:-walker_f,cheetah_f,hopper_f,snake_f,dartb}
 rm -rf dart_env_b200/build$sfx dart_env_b200/libdartb$sfx.so
 cp -r dart_env_b200/build dart_env_b200/build$sfx
 DARTB_SO_SUFFIX=$sfx DARTB_NVCC_FLAGS="$*" DARTB_BUILD_ONLY=$only python -m dart_env_b200.build > /dev/null
