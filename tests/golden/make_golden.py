@@ -97,19 +97,44 @@ def env_rollouts(env_id, n_steps, scales, seed):
     env = getattr(importlib.import_module(mod), cls)()
     env.seed(seed)
     rng = np.random.RandomState(seed)
-    rec = {k: [] for k in ("q", "dq", "action", "obs", "reward", "done", "q2", "dq2", "margin", "reset_obs")}
+    rec = {k: [] for k in ("q", "dq", "action", "obs", "reward", "done", "q2", "dq2", "margin", "reset_obs", "event_margin")}
+    # distance of every DISCRETE decision taken inside an env step (contact on/off per capsule, flat-capsule end tie,
+    # joint limit on/off, over all frame_skip DART steps) from its threshold: the fp32 parity tests assert a MAX error
+    # over the samples whose decisions are not within rounding of flipping, and tag the rest
+    m = build_model(env_id)
+    limits = [(d, m.bodies[bi].q_lo, m.bodies[bi].q_hi) for d, bi in enumerate(m.dof_bodies()) if m.bodies[bi].limit_enforced]
+    world = env.dart_world
+    orig_step = world.step
+    ev = {"m": np.inf}
+
+    def step_hook():
+        q_pre = world._ow.get_state()[0].copy()
+        orig_step()
+        gaps, tilts = world._ow.shape_gaps()
+        mg = [np.inf]
+        if len(gaps):
+            mg.append(float(np.min(np.abs(gaps))))
+            if (gaps <= 0).any():
+                mg.append(float(np.min(tilts[gaps <= 0])))
+        for d, lo, hi in limits:
+            mg += [abs(q_pre[d] - lo), abs(q_pre[d] - hi)]
+        ev["m"] = min(ev["m"], min(mg))
+
+    world.step = step_hook
     for scale in scales:
         ob = env.reset()
         rec["reset_obs"].append(np.concatenate([env.state_vector(), ob]))
         for t in range(n_steps):
             a = rng.uniform(-1.3, 1.3, spec.task.n_act) * scale  # beyond +-1: exercises the clamp
             s0 = env.state_vector()
+            ev["m"] = np.inf
             ob, r, d, _ = env.step(a)
             s1 = env.state_vector()
             nd = len(s0) // 2
             rec["q"].append(s0[:nd]); rec["dq"].append(s0[nd:]); rec["action"].append(a)
             rec["obs"].append(ob); rec["reward"].append(r); rec["done"].append(d)
             rec["q2"].append(s1[:nd]); rec["dq2"].append(s1[nd:]); rec["margin"].append(done_margin(spec, env))
+            rec["event_margin"].append(ev["m"])
             if d:
                 ob = env.reset()
     return {"step_" + k: np.array(v) for k, v in rec.items()}

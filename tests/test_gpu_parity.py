@@ -1,16 +1,19 @@
 """GPU parity tests (run on the B200 box): the CUDA path, called through the C-ABI, against
 the CPU oracle and the committed golden vectors.
 
-Tolerances (stated, per north_star "fp32 tolerance; bit-exact contact-pair sets and done flags"):
-  fp64 kernel instantiation vs oracle (same algorithm, different formulation):  1e-9 rel
-  fp32 product path, single DART step from identical (q, dq, tau), error relative to (1 + |x|):
-        dq : median < 5e-6, 99th percentile < 5e-4, max < 5e-2
-        q  : max < 2e-4
-     (the max is reached only on the goldens' unphysical deep-penetration multi-contact states:
-      contact impulses amplify fp32 rounding through A^-1 and cond(A) reaches 1/CFM = 1e5)
-  fp32 env.step (4-5 sub-steps): obs/dq 2e-3 * (1 + |x|), reward 2e-3 * (1 + |r|)
-  contact-pair index sets, limit sets and done flags: bit-exact on every sample that is not
-  within 1e-4 of a contact / limit / termination threshold (those are tagged in the goldens).
+Tolerances (stated once here and in DESIGN.md §2b; per north_star "fp32 tolerance; bit-exact contact-pair sets and
+done flags").  All errors are MAXIMA over every sample outside the explicitly tagged classes, relative to (1 + |x|):
+  fp64 kernel instantiation vs oracle (same algorithm, different formulation):  1e-9
+  fp32 product path, single DART step from identical (q, dq, tau):   dq 2e-4 (TOL_SUB_DQ), q 1e-5 (TOL_SUB_Q)
+  fp32 env.step (4-5 DART steps + task layer):   obs 2e-4 (TOL_STEP_OBS), reward 1e-3 (TOL_STEP_REW)
+  contact-pair index sets, limit sets and done flags: bit-exact.
+Tagged classes (the goldens carry the tags; nothing else is excluded):
+  margin   a discrete decision (contact on/off, flat-capsule end tie, joint limit on/off, termination threshold)
+           sits within MARGIN = 1e-4 of its threshold, so fp32 rounding may legitimately flip it;
+  deep     a hand-built contact sweep state with a capsule more than DEEP = 0.03 m inside the ground (30x the
+           velocity-correction cap): contact impulses amplify rounding through A^-1, cond(A) -> 1/CFM = 1e5.  These stay
+           bounded by TOL_SUB_DQ_DEEP = 2e-2 and keep their bit-exact contact sets.
+Every test prints p50 / p99 / max of what it measured (pytest -s, and gpurun_out/parity_errors.log when writable).
 """
 import os
 
@@ -27,6 +30,23 @@ FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
          "DartHalfCheetah-v1": "halfcheetah.npz", "DartSnake7Link-v1": "snake7link.npz"}
 ENVS = list(SPECS)
 MARGIN = 1e-4
+DEEP = 0.03
+TOL_SUB_DQ, TOL_SUB_Q, TOL_SUB_DQ_DEEP = 2e-4, 1e-5, 2e-2
+TOL_STEP_OBS, TOL_STEP_REW = 2e-4, 1e-3
+
+
+def _report(name, env_id, err):
+    err = np.asarray(err, dtype=np.float64).ravel()
+    line = "%-34s %-20s variant=%s n=%4d p50 %.2e p99 %.2e max %.2e" % (
+        name, env_id, VARIANT, err.size, np.median(err), np.percentile(err, 99), err.max())
+    print(line)
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, "parity_errors.log"), "a") as f:
+                f.write(line + "\n")
+    except OSError:
+        pass
 
 
 VARIANT = 0   # this module pins the one-world-per-thread kernels; tests/test_gpu_coop.py re-runs its tests with the
@@ -111,12 +131,16 @@ def test_substep_fp32_within_stated_tolerance(models, env_id):
     assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
     mc = min(body.shape[1], g["sub_contact_body"].shape[1])
     assert np.array_equal(body[safe, :mc], g["sub_contact_body"][safe, :mc])
-    eq = np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"]))
-    ev = np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"]))
-    assert eq[safe].max() < 2e-4, eq[safe].max()
-    assert ev[safe].max() < 5e-2, ev[safe].max()
-    assert np.percentile(ev[safe].max(1), 99) < 5e-4
-    assert np.median(ev[safe].max(1)) < 5e-6
+    eq = (np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"]))).max(1)
+    ev = (np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"]))).max(1)
+    deep = g["sub_contact_data"][:, :, 6].max(1) > DEEP
+    _report("substep dq (not deep)", env_id, ev[safe & ~deep])
+    _report("substep q", env_id, eq[safe])
+    assert ev[safe & ~deep].max() < TOL_SUB_DQ, ev[safe & ~deep].max()
+    assert eq[safe].max() < TOL_SUB_Q, eq[safe].max()
+    if (safe & deep).any():
+        _report("substep dq (deep penetration)", env_id, ev[safe & deep])
+        assert ev[safe & deep].max() < TOL_SUB_DQ_DEEP, ev[safe & deep].max()
 
 
 def _envstep(models, env_id, g, f64):
@@ -156,10 +180,16 @@ def test_env_step_matches_reference_task_layer(models, env_id):
     obs, rew, done, q2, dq2 = _envstep(models, env_id, g, False)
     safe = fin & (g["step_margin"] > MARGIN)
     assert np.array_equal(done[safe], g["step_done"][safe].astype(bool))
-    eo = np.abs(obs - g["step_obs"])[fin] / (1 + np.abs(g["step_obs"][fin]))
-    er = np.abs(rew - g["step_reward"])[fin] / (1 + np.abs(g["step_reward"][fin]))
-    assert np.percentile(eo.max(1), 90) < 2e-3 and np.percentile(er, 90) < 2e-3
-    assert np.median(eo.max(1)) < 1e-5
+    # maxima over every sample whose discrete decisions (contact / tie / limit, in any of the frame_skip DART steps)
+    # are not within MARGIN of flipping
+    ok = fin & (g["step_event_margin"] > MARGIN)
+    assert ok.sum() > 0.4 * len(ok)
+    eo = (np.abs(obs - g["step_obs"]) / (1 + np.abs(g["step_obs"])))[ok].max(1)
+    er = (np.abs(rew - g["step_reward"]) / (1 + np.abs(g["step_reward"])))[ok]
+    _report("env.step obs", env_id, eo)
+    _report("env.step reward", env_id, er)
+    assert eo.max() < TOL_STEP_OBS, eo.max()
+    assert er.max() < TOL_STEP_REW, er.max()
 
 
 @pytest.mark.parametrize("env_id", ENVS)

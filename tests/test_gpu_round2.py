@@ -1,0 +1,271 @@
+"""GPU tests added in round 2 (run on the B200 box, through the C-ABI): product paths that had no test —
+the fp32 contact-free envs against the reference-class goldens, the perturbation branch of do_simulation
+(dart_env.py:159-172) against the oracle's add_ext_force, every host-buffer route of dartb_step_host /
+dartb_step_host_gym (page-locked zero-copy, pageable staging, DARTB_ZEROCOPY=0 copies), the full-row-count
+constraint set (every capsule touching and every limit active: no row may be dropped), the opt-in contact
+read-back, dartb_seed, and the pinned output pool of the batched host API."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from dart_env_b200.tasks import SPECS
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CF = {"DartCartPole-v1": "cartpole.npz", "DartCartPoleSwingUp-v1": "cartpole_swingup.npz",
+      "DartDoubleInvertedPendulumEnv-v1": "double_pendulum.npz", "DartReacher-v1": "reacher2d.npz"}
+TOL_CF = 2e-4   # fp32 contact-free env.step, max over all samples, relative to (1 + |x|)
+
+
+def _make(env_id, **kw):
+    from dart_env_b200.envs import make
+    return make(env_id, **kw)
+
+
+@pytest.mark.parametrize("env_id", list(CF))
+def test_contact_free_envs_fp32_match_reference_classes(env_id):
+    """the fp32 PRODUCT path of the four contact-free envs against goldens minted from the reference's own classes"""
+    g = np.load(os.path.join(GOLD, CF[env_id]))
+    n = len(g["step_q"])
+    env = _make(env_id, num_envs=n, output="numpy", seed=0, auto_reset=False)
+    assert "/f32" in env.engine.kernel_name
+    env.set_state(g["step_q"], g["step_dq"])
+    if env_id == "DartReacher-v1":
+        env.set_target(g["step_target"])
+    ob, rew, done, _ = env.step(g["step_action"])
+    s = env.state_vector()
+    nd = g["step_q"].shape[1]
+    rel = lambda a, b: (np.abs(a - b) / (1 + np.abs(b))).max()
+    assert rel(s[:, :nd], g["step_q2"]) < TOL_CF and rel(s[:, nd:], g["step_dq2"]) < TOL_CF
+    assert rel(ob, g["step_obs"]) < TOL_CF
+    assert rel(rew, g["step_reward"]) < 5 * TOL_CF
+    # done flags bit-exact away from the thresholds (|angle| = 0.2 for the cart-pole, height = 1 for the pendulum)
+    if env_id == "DartCartPole-v1":
+        safe = np.abs(np.abs(g["step_obs"][:, 1]) - 0.2) > 1e-4
+    else:
+        safe = np.ones(n, dtype=bool)
+    assert np.array_equal(done[safe], g["step_done"][safe].astype(bool))
+    env.close()
+
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_add_perturbation_matches_oracle_ext_force(f64):
+    """dart_env.py:159-172: the drawn force is applied with add_ext_force at the origin of bodynodes[bodyid] on every
+    sub-step of the call.  Compared with the oracle's add_ext_force on the same force."""
+    from oracle import oracle as orc
+    env_id = "DartHopper-v1"
+    spec = SPECS[env_id]
+    n = 32
+    env = _make(env_id, num_envs=n, output="numpy", seed=4, auto_reset=False, f64=f64, kernel_variant=0)
+    env.reset()
+    env.add_perturbation = True
+    env.perturbation_parameters = [1.0, 7.5, 3]   # always draw; magnitude; body id
+    q0, dq0 = (x.cpu().numpy() for x in env.engine.get_state(torch.float64))
+    rng = np.random.RandomState(0)
+    tau = np.zeros((n, env.model.n_dofs))
+    tau[:, 3:] = rng.uniform(-50, 50, (n, 3))
+    env.do_simulation(tau, env.frame_skip)
+    f = env.perturb_force.cpu().numpy().astype(np.float64)
+    assert (np.abs(f).sum(1) == 7.5).all() and (f[:, 2] == 0).all()     # +-magnitude along x or y
+    q1, dq1 = (x.cpu().numpy() for x in env.engine.get_state(torch.float64))
+    worst = 0.0
+    for w in range(n):
+        ow = orc.OracleWorld(env.model)
+        ow.set_state(q0[w], dq0[w])
+        for _ in range(env.frame_skip):
+            ow.add_ext_force(3, f[w])
+            ow.set_forces(tau[w])
+            ow.step()
+        oq, odq = ow.get_state()
+        worst = max(worst, float((np.abs(dq1[w] - odq) / (1 + np.abs(odq))).max()), float(np.abs(q1[w] - oq).max()))
+    assert worst < (1e-8 if f64 else 2e-4), worst
+    # the force really acted: without it the result differs
+    env2 = _make(env_id, num_envs=n, output="numpy", seed=4, auto_reset=False, f64=f64, kernel_variant=0)
+    env2.reset()
+    env2.do_simulation(tau, env2.frame_skip)
+    assert np.abs(env2.state_vector()[:, env.model.n_dofs:] - dq1).max() > 1e-3
+    # the fused step() does not draw perturbations: it must refuse rather than ignore the flag
+    with pytest.raises(NotImplementedError):
+        env.step(np.zeros((n, 3), dtype=np.float32))
+    env.close(); env2.close()
+
+
+def _host_step_outputs(env_id, n, seed, route):
+    """one env.step() through a host-buffer route; returns (obs, reward, done) as float64/bool numpy"""
+    from dart_env_b200.engine import Engine
+    from dart_env_b200.skel import load_model
+    spec = SPECS[env_id]
+    m = load_model(spec.skel, spec.dt)
+    m.enforce_limits()
+    eng = Engine(m, spec.task, n, seed=seed)
+    eng.reset()
+    rng = np.random.RandomState(5)
+    act = rng.uniform(-1, 1, (n, spec.task.n_act)).astype(np.float32)
+    for _ in range(3):   # a few steps so contacts exist
+        if route == "device":
+            obs = torch.empty((n, spec.task.n_obs), dtype=torch.float32, device="cuda")
+            rew = torch.empty((n,), dtype=torch.float32, device="cuda")
+            done = torch.empty((n,), dtype=torch.uint8, device="cuda")
+            eng.step(torch.tensor(act, device="cuda"), obs, rew, done, True)
+            torch.cuda.synchronize()
+            out = obs.cpu().numpy(), rew.cpu().numpy().astype(np.float64), (done.cpu().numpy() & 1).astype(bool)
+        elif route in ("pageable", "pinned"):
+            mk = (lambda *sh, dt: torch.empty(sh, dtype=dt).pin_memory().numpy()) if route == "pinned" else \
+                 (lambda *sh, dt: torch.empty(sh, dtype=dt).numpy())
+            a = mk(n, spec.task.n_act, dt=torch.float32); a[:] = act
+            obs, rew, done = mk(n, spec.task.n_obs, dt=torch.float32), mk(n, dt=torch.float32), mk(n, dt=torch.uint8)
+            eng.step_host(a, obs, rew, done, True)
+            out = obs.copy(), rew.astype(np.float64), (done & 1).astype(bool)
+        else:   # gym types: float64 rewards, bool dones; pageable or pinned outputs
+            pin = route == "gym_pinned"
+            mk = (lambda *sh, dt: torch.empty(sh, dtype=dt).pin_memory().numpy()) if pin else (lambda *sh, dt: torch.empty(sh, dtype=dt).numpy())
+            obs, rew = mk(n, spec.task.n_obs, dt=torch.float32), mk(n, dt=torch.float64)
+            done = mk(n, dt=torch.uint8)
+            import ctypes as C
+            from dart_env_b200 import capi
+            capi.check(eng.L.dartb_step_host_gym(eng.h, C.c_void_p(act.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                                 C.c_void_p(rew.ctypes.data), C.c_void_p(done.ctypes.data), None, 1, eng._stream()))
+            assert set(np.unique(done)) <= {0, 1}
+            out = obs.copy(), rew.copy(), done.astype(bool)
+    eng.close()
+    return out
+
+
+def test_every_host_buffer_route_equals_the_device_path():
+    """dartb_step_host with page-locked (zero-copy) and pageable (staging) buffers, dartb_step_host_gym with both: the
+    same bits as dartb_step on device buffers."""
+    ref = _host_step_outputs("DartHopper-v1", 300, 6, "device")
+    for route in ("pinned", "pageable", "gym_pinned", "gym_pageable"):
+        o, r, d = _host_step_outputs("DartHopper-v1", 300, 6, route)
+        assert np.array_equal(o, ref[0]) and np.array_equal(r, ref[1]) and np.array_equal(d, ref[2]), route
+
+
+def test_zerocopy_off_copy_path_equals_the_device_path():
+    """DARTB_ZEROCOPY=0 (explicit H2D / D2H copies) is read once per process: run it in a child."""
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; from tests.test_gpu_round2 import _host_step_outputs as f\n"
+            "ref = f('DartHopper-v1', 300, 6, 'device')\n"
+            "for route in ('pinned', 'pageable', 'gym_pageable'):\n"
+            "    o, r, d = f('DartHopper-v1', 300, 6, route)\n"
+            "    assert np.array_equal(o, ref[0]) and np.array_equal(r, ref[1]) and np.array_equal(d, ref[2]), route\n"
+            "print('copy-path ok')\n") % ROOT
+    env = dict(os.environ, DARTB_ZEROCOPY="0")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "copy-path ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("env_id", ["DartHopper-v1", "DartWalker2d-v1", "DartHalfCheetah-v1"])
+@pytest.mark.parametrize("variant", [0, 2])
+def test_full_constraint_set_no_row_dropped(env_id, variant):
+    """Adversarial state: the skeleton lies in the ground with EVERY capsule touching and EVERY enforced limit violated,
+    i.e. the maximum row count 2*NS + NL of the topology.  The fp64 kernels must reproduce the oracle's step (a silently
+    dropped row would change dq by O(1)), and the contact count must be the capsule count."""
+    from dart_env_b200.engine import Engine
+    from dart_env_b200.skel import load_model
+    from oracle import oracle as orc
+    spec = SPECS[env_id]
+    m = load_model(spec.skel, spec.dt)
+    m.enforce_limits()
+    nd = m.n_dofs
+    rng = np.random.RandomState(3)
+    NR = 2 * len(m.shapes) + sum(b.limit_enforced for b in m.bodies)
+    cand = []
+    ow = orc.OracleWorld(m)
+    for trial in range(4000):
+        q = np.array(m.q_init(), dtype=float)
+        q[2] = rng.choice([-1.57, 1.57]) + rng.uniform(-0.15, 0.15)   # lying down
+        q[1] = rng.uniform(-1.5, -0.6)
+        for d, bi in enumerate(m.dof_bodies()):
+            b = m.bodies[bi]
+            if b.limit_enforced:
+                if rng.rand() < 0.8:   # violate the limit that keeps the limb straighter
+                    lim = b.q_lo if abs(b.q_lo) < abs(b.q_hi) else b.q_hi
+                    q[d] = lim + np.sign(lim if lim != 0 else (1 if lim is b.q_hi else -1)) * rng.uniform(0.0, 0.02)
+                    if lim == 0:
+                        q[d] = rng.uniform(0.0, 0.02) * (1 if b.q_hi == 0 else -1)
+                else:
+                    q[d] = rng.uniform(b.q_lo, b.q_hi)
+        dq = rng.uniform(-1, 1, nd)
+        ow.set_state(q, dq); ow.set_forces(np.zeros(nd)); ow.step()
+        if ow.lcp_failed():
+            continue
+        # rows in the planar kernels' terms: (normal, in-plane tangent) per contact + active limits (the oracle also
+        # carries the inert out-of-plane tangent row of every contact)
+        cand.append((2 * len(ow.contacts()) + int((ow.limit_active() != 0).sum()), trial, q, dq, ow.get_state()[1].copy(), len(ow.contacts())))
+    cand.sort(key=lambda c: -c[0])
+    S = [(c[2], c[3], c[4], c[0], c[5]) for c in cand[:8]]
+    print("%s: largest row counts found %s of NR = %d" % (env_id, [c[0] for c in cand[:8]], NR))
+    assert S[0][3] >= NR - (6 if env_id == "DartHalfCheetah-v1" else 0)   # hopper, walker: the FULL set, 2*NS + NL rows
+    q, dq, ref = (np.array([s[k] for s in S]) for k in range(3))
+    nrows = max(s[3] for s in S)
+    eng = Engine(m, spec.task, len(S), f64=True, kernel_variant=variant)
+    eng.set_state(torch.tensor(q, device="cuda"), torch.tensor(dq, device="cuda"))
+    eng.substep(torch.zeros((len(S), nd), dtype=torch.float64, device="cuda"))
+    _, dq2 = eng.get_state(torch.float64)
+    cnt, body, data = eng.contacts()
+    torch.cuda.synchronize()
+    assert np.array_equal(cnt.cpu().numpy(), np.array([s[4] for s in S]))
+    err = np.abs(dq2.cpu().numpy() - ref).max()
+    assert err < 1e-6, (err, nrows)
+    eng.close()
+
+
+def test_contact_readback_is_opt_in():
+    from dart_env_b200 import capi
+    env = _make("DartWalker2d-v1", num_envs=64, output="torch", seed=1)
+    env.reset()
+    env.step(torch.zeros((64, 6), device="cuda"))
+    with pytest.raises(capi.DartbError):
+        env.contacts()
+    env.do_simulation(np.zeros((64, 9)), 1)     # the literal World.step() always refreshes collision_result
+    assert env.contacts()[0].shape == (64,)
+    env.engine.set_contacts(True)
+    env.step(torch.zeros((64, 6), device="cuda"))
+    assert env.contacts()[0].shape == (64,)
+    env.close()
+
+
+def test_seed_rekeys_reset_noise_without_touching_state():
+    from oracle import oracle as orc
+    env_id = "DartHopper-v1"
+    env = _make(env_id, num_envs=16, output="torch", seed=10)
+    env.reset()
+    q0, _ = env.engine.get_state(torch.float64)
+    env.seed(77)
+    q1, _ = env.engine.get_state(torch.float64)
+    assert torch.equal(q0, q1)                   # dart_env.py:117-119: seeding only reseeds
+    env.reset()                                  # second episode of every world, drawn under the new key
+    q2, _ = env.engine.get_state(torch.float64)
+    for w in (0, 5, 15):
+        expect = [np.float32(env.model.q_init()[i]) + np.float32(orc.reset_uniform(77, w, 1, i)) * np.float32(0.005)
+                  for i in range(env.model.n_dofs)]
+        assert np.array_equal(q2[w].cpu().numpy().astype(np.float32), np.array(expect, dtype=np.float32))
+    env.close()
+
+
+def test_batched_host_step_returns_fresh_arrays_of_reference_types():
+    """VectorEnv(copy=True) semantics on the pinned output pool: arrays the caller keeps are never overwritten."""
+    env = _make("DartHopper-v1", num_envs=128, output="numpy", seed=3)
+    env.reset()
+    rng = np.random.RandomState(0)
+    kept = []
+    for i in range(6):
+        o, r, d, info = env.step(rng.uniform(-1, 1, (128, 3)).astype(np.float32))
+        assert o.dtype == np.float32 and r.dtype == np.float64 and d.dtype == np.bool_ and "TimeLimit.truncated" in info
+        kept.append((o, o.copy(), r, r.copy(), d, d.copy()))
+    for o, oc, r, rc, d, dc in kept:
+        assert np.array_equal(o, oc) and np.array_equal(r, rc) and np.array_equal(d, dc)
+    assert len({id(k[0]) for k in kept}) == 6
+    view = kept[0][0][3]            # a VIEW keeps its slot out of circulation too
+    del kept
+    vc = view.copy()
+    for i in range(80):
+        env.step(rng.uniform(-1, 1, (128, 3)).astype(np.float32))
+    assert np.array_equal(view, vc)
+    assert len(env._pool.slots) <= 4
+    env.close()

@@ -73,6 +73,12 @@ elif mode == "xover":   # both forms right at the automatic crossover sizes
     for env_id, n in (("DartHopper-v1", 4736), ("DartWalker2d-v1", 6144), ("DartHalfCheetah-v1", 12288), ("DartSnake7Link-v1", 2368)):
         for v in ("0", "2"):
             cfgs.append((env_id, n, "128", v))
+elif mode == "r2big":   # round 2: the large-batch per-thread kernels, launch shapes x exact / PGS
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384)):
+        for b, wpw, pgs in (("32", "", ""), ("128", "", ""), ("32", "16", ""), ("32", "8", ""), ("128", "", "30")):
+            cfgs.append((env_id, n, b, "0", pgs, wpw))
+    cfgs.append(("DartHopper-v1", 65536, "128", "0"))
+    cfgs.append(("DartHopper-v1", 4096, "32", "0"))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):
