@@ -71,6 +71,7 @@ struct dartb_engine {
     PTask<float> tf; PTask<double> td;
     dartb_model_t model; dartb_task_t task;   // kept so friction/options can re-lower
     void* q = nullptr; void* dq = nullptr;
+    void* aux = nullptr;                      // [3][n] of Real: per-world task state (reacher target), or null
     void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
     uint64_t* hint = nullptr;                 // LCP warm-start sets, see planar_kernels.cuh::substep
@@ -118,7 +119,7 @@ static int lower_into(dartb_engine* e) {
     const int forced_variant = envcfg().variant;
     const int want = e->variant_request >= 0 ? e->variant_request : forced_variant;
     const bool coop_ok = !(res.t.fluid_force && res.m.ns > 0);   // no cooperative fluid kernel for topologies with capsules
-    if (topo < 0 || res.m.any_coulomb || want == 1) e->variant = 1;
+    if (topo < 0 || res.m.any_coulomb || want == 1 || res.t.kind != DARTB_TASK_LOCOMOTION) e->variant = 1;
     else if (want == 2 && coop_ok) e->variant = 2;
     else if (!coop_ok) e->variant = 0;
     else if (want == 0) e->variant = 0;
@@ -188,6 +189,7 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.n = e->n; a.q = (R*)e->q; a.dq = (R*)e->dq; a.episode = e->episode; a.elapsed = e->elapsed;
     a.truncated = e->truncated;
     a.hint = e->hint;
+    a.aux = (R*)e->aux;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset;
     if (e->contacts) { a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; }
@@ -323,6 +325,14 @@ static int create_impl(const dartb_model_t* model, const dartb_task_t* task, int
     A((void**)&e->episode, 4 * (size_t)n); A((void**)&e->elapsed, 4 * (size_t)n); A((void**)&e->truncated, (size_t)n);
     A((void**)&e->hint, 8 * (size_t)n);
     if (err == cudaSuccess) err = cudaMemset(e->hint, 0xFF, 8 * (size_t)n);
+    if (task->kind == DARTB_TASK_REACHER2D) {
+        A(&e->aux, rs * 3 * (size_t)n);
+        // self.target = [0.1, 0.01, -0.1] until the first reset draws one (reacher2d.py:7)
+        const double t0[3] = {0.1, 0.01, -0.1};
+        std::vector<double> hd(3 * (size_t)n); std::vector<float> hf(3 * (size_t)n);
+        for (int c = 0; c < 3; c++) for (int w = 0; w < n; w++) { hd[(size_t)c * n + w] = t0[c]; hf[(size_t)c * n + w] = (float)t0[c]; }
+        if (err == cudaSuccess) err = cudaMemcpy(e->aux, f64 ? (const void*)hd.data() : (const void*)hf.data(), rs * 3 * (size_t)n, cudaMemcpyHostToDevice);
+    }
     A((void**)&e->ccount, 4 * (size_t)n); A((void**)&e->cbody, 4 * (size_t)n * e->max_contacts);
     A((void**)&e->cdata, 4 * (size_t)n * e->max_contacts * 10);
     if (err != cudaSuccess) { dartb_destroy(e); return fail(std::string("cudaMalloc: ") + cudaGetErrorString(err)); }
@@ -389,7 +399,7 @@ int dartb_create_f64(const dartb_model_t* model, const dartb_task_t* task, int32
 int dartb_destroy(dartb_handle_t e) {
     if (!e) return 0;
     DeviceGuard g(e->device);
-    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
+    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->aux); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
     cudaFree(e->truncated); cudaFree(e->hint); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
     if (e->coop_tab) cudaFree(e->coop_tab);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -639,6 +649,29 @@ int dartb_substep_f64(dartb_handle_t e, const double* d_tau, const double* d_fex
     if (d_tau) { size_t k = (size_t)e->n * e->nd; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_tau, sc); tau = sc; e->launches++; }
     if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sf); fx = sf; e->launches++; }
     return launch_substep<float>(e, tau, fx, st);
+}
+
+int dartb_set_aux(dartb_handle_t e, const double* d_aux, void* stream) {
+    if (!e || !d_aux) return fail("null argument");
+    if (!e->aux) return fail("this task kind has no auxiliary per-world state");
+    DeviceGuard g(e->device);
+    const int tot = e->n * 3, bs = 256, grid = (tot + bs - 1) / bs;
+    if (e->f64) k_to_soa<double, double><<<grid, bs, 0, (cudaStream_t)stream>>>(e->n, 3, d_aux, (double*)e->aux);
+    else k_to_soa<double, float><<<grid, bs, 0, (cudaStream_t)stream>>>(e->n, 3, d_aux, (float*)e->aux);
+    e->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int dartb_get_aux(dartb_handle_t e, double* d_aux, void* stream) {
+    if (!e || !d_aux) return fail("null argument");
+    if (!e->aux) return fail("this task kind has no auxiliary per-world state");
+    DeviceGuard g(e->device);
+    const int tot = e->n * 3, bs = 256, grid = (tot + bs - 1) / bs;
+    if (e->f64) k_from_soa<double, double><<<grid, bs, 0, (cudaStream_t)stream>>>(e->n, 3, (const double*)e->aux, d_aux);
+    else k_from_soa<float, double><<<grid, bs, 0, (cudaStream_t)stream>>>(e->n, 3, (const float*)e->aux, d_aux);
+    e->launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int dartb_get_contacts(dartb_handle_t e, int32_t* d_count, int32_t* d_body, float* d_data, void* stream) {

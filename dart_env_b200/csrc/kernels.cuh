@@ -9,6 +9,7 @@
 #include "planar_kernels.cuh"
 #include "planar_loop.cuh"
 #include "planar_coop.cuh"
+#include "task_kinds.cuh"
 
 // resident blocks (of 128 threads) per SM the per-thread kernels are compiled for: 1 = up to 255 registers
 #ifndef DARTB_STEP_MIN_BLOCKS
@@ -335,10 +336,38 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     }
     __syncwarp();
     const R posbefore = q[0];
+    R tg[3] = {0, 0, 0};
+    if (a.aux && active) { tg[0] = a.aux[w]; tg[1] = a.aux[(size_t)a.n + w]; tg[2] = a.aux[2 * (size_t)a.n + w]; }
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (active && f == K.frame_skip - 1 && a.sink.count) ? &a.sink : nullptr;
         substep_loop<R>(M, q, dq, tau, false, tau, tau, tau, K.fluid_force != 0, K.fluid_offset, K.fluid_coef, a.lcp_mode,
                         a.pgs_iters, sk, w);
+    }
+    if (K.kind != DARTB_TASK_LOCOMOTION) {
+        // the contact-free envs: their own reward / done / reset / obs formulas, same TimeLimit and auto-reset plumbing
+        R r; bool done, trunc = false;
+        task_kind_eval<R>(M, K, q, dq, tg, a2, r, done);
+        if (active && a.max_episode_steps > 0) {
+            const int el = a.elapsed[w] + 1;
+            if (el >= a.max_episode_steps) { trunc = !done; done = true; }
+            a.elapsed[w] = (done && a.auto_reset) ? 0 : el;
+        }
+        if (active && done && a.auto_reset) {
+            const uint32_t ep = a.episode[w];
+            reset_state_kind<R>(M, K, a.seed, a.world_offset + w, ep, q, dq, tg);
+            a.episode[w] = ep + 1;
+            if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
+        }
+        if (active) write_obs_kind<R>(M, K, q, dq, tg, sw + lane * K.n_obs);
+        __syncwarp();
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+        if (active) {
+            for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
+            if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
+            else { a.reward[w] = (float)r; a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0)); }
+            if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
+        }
+        return;
     }
     const R ang = q[2];
     R r = (q[0] - posbefore) * K.inv_dt_env * K.vel_weight;
@@ -405,9 +434,15 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
         q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
         dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
     }
+    R tg[3] = {0, 0, 0};
+    if (a.aux && active) { tg[0] = a.aux[w]; tg[1] = a.aux[(size_t)a.n + w]; tg[2] = a.aux[2 * (size_t)a.n + w]; }
     if (doit) {
         const uint32_t ep = a.episode[w];
-        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        if (K.kind == DARTB_TASK_LOCOMOTION) reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        else {
+            reset_state_kind<R>(M, K, a.seed, a.world_offset + w, ep, q, dq, tg);
+            if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
+        }
         a.episode[w] = ep + 1;
         a.elapsed[w] = 0;
         a.hint[w] = ~(uint64_t)0;
@@ -415,7 +450,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
         if (a.sink.count) a.sink.count[w] = 0;
     }
     if (a.obs) {
-        if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
+        if (active) { if (K.kind == DARTB_TASK_LOCOMOTION) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs); else write_obs_kind<R>(M, K, q, dq, tg, sw + lane * K.n_obs); }
         __syncwarp();
         if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
     }

@@ -308,8 +308,29 @@ static std::string lower_model(const dartb_model_t& dm, const dartb_task_t& dt_,
         t.dof_scale[d] = dt_.act_scale[i]; t.dof_lo[d] = dt_.act_lo[i]; t.dof_hi[d] = dt_.act_hi[i];
     }
     t.obs_mode = dt_.obs_mode;
+    t.kind = dt_.kind;
+    t.noise_dq = dt_.reset_noise_dq >= 0 ? dt_.reset_noise_dq : dt_.reset_noise;
     int expect = (dt_.obs_mode == DARTB_OBS_HEIGHT_Q2_DQ) ? (1 + (nb - 2) + nb) : ((nb - 1) + nb);
-    if (dt_.n_obs != expect) return "n_obs does not match obs_mode";
+    int nprobe = 0;
+    switch (dt_.kind) {
+        case DARTB_TASK_LOCOMOTION: break;
+        case DARTB_TASK_CARTPOLE: case DARTB_TASK_SWINGUP: expect = 2 * nb; break;
+        case DARTB_TASK_DOUBLE_PENDULUM: expect = 1 + 2 * (nb - 1) + nb; nprobe = 2; break;
+        case DARTB_TASK_REACHER2D: expect = 2 * nb + 2 + nb + 3; nprobe = 1; break;
+        default: return "unknown task kind";
+    }
+    if (dt_.n_obs != expect) return "n_obs does not match the task's observation layout";
+    if (dt_.kind != DARTB_TASK_LOCOMOTION && (nb < 2 || dt_.fluid_force)) return "contact-free task kinds need >= 2 dofs and no fluid force";
+    for (int k = 0; k < 2; k++) {
+        t.probe_body[k] = 0; t.probe_x[k] = 0; t.probe_y[k] = 0; t.probe_n[k] = 0;
+        if (k >= nprobe) continue;
+        int pb = dt_.probe_body[k];
+        if (pb < 0 || pb >= nbd) return "probe body out of range";
+        V3 C = apply(Tw[pb], v3(dt_.probe_local[k][0], dt_.probe_local[k][1], dt_.probe_local[k][2]));
+        V3 d = C - P0[group[pb]];
+        t.probe_body[k] = group[pb];
+        t.probe_x[k] = dot(e1, d); t.probe_y[k] = dot(e2, d); t.probe_n[k] = dot(en, C);
+    }
     t.dq_clip = dt_.dq_clip;
     t.height_body = -1;
     if (dt_.height_body >= 0) {
@@ -334,7 +355,7 @@ static std::string lower_model(const dartb_model_t& dm, const dartb_task_t& dt_,
     t.fluid_offset = dt_.fluid_offset; t.fluid_coef = dt_.fluid_coef;
     t.reset_noise = dt_.reset_noise; t.state_bound = dt_.state_bound;
     t.inv_dt_env = 1.0 / (dm.dt * dt_.frame_skip);
-    if (nb < 3) return "task layer needs at least 3 dofs (q[0], q[2] are read)";
+    if (dt_.kind == DARTB_TASK_LOCOMOTION && nb < 3) return "task layer needs at least 3 dofs (q[0], q[2] are read)";
     return "";
 }
 
@@ -382,6 +403,10 @@ static void convert(const PTask<double>& a, PTask<R>& b) {
     b.zero_reward_on_blowup = a.zero_reward_on_blowup; b.fluid_force = a.fluid_force;
     b.fluid_offset = (R)a.fluid_offset; b.fluid_coef = (R)a.fluid_coef;
     b.reset_noise = (R)a.reset_noise; b.state_bound = (R)a.state_bound; b.inv_dt_env = (R)a.inv_dt_env;
+    b.kind = a.kind; b.noise_dq = (R)a.noise_dq;
+    for (int k = 0; k < 2; k++) {
+        b.probe_body[k] = a.probe_body[k]; b.probe_x[k] = (R)a.probe_x[k]; b.probe_y[k] = (R)a.probe_y[k]; b.probe_n[k] = (R)a.probe_n[k];
+    }
 }
 
 }  // namespace lower

@@ -1033,6 +1033,7 @@ struct StepArgs {
     uint8_t* done;       // [n]
     double* reward64;    // gym return types (sync_vector_env.py:44-47): when set, rewards go HERE as float64 and `done`
                          // receives plain 0/1 bools (the truncation flag only in `truncated`)
+    R* aux;              // [3][n] per-world task state (DARTB_TASK_REACHER2D target: world x, y, z) or null
     const uint8_t* mask; // reset mask (k_reset) or null
     int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
     int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for

@@ -81,4 +81,10 @@ struct PTask {
     R fluid_offset, fluid_coef;
     R reset_noise, state_bound;
     R inv_dt_env;
+    // contact-free task kinds (DARTB_TASK_*): probes = body-fixed points whose world position the task reads
+    int32_t kind;
+    R noise_dq;                // reset noise on dq
+    int32_t probe_body[2];     // planar body
+    R probe_x[2], probe_y[2];  // point in that planar body frame
+    R probe_n[2];              // its (constant) out-of-plane coordinate
 };

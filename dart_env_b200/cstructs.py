@@ -13,6 +13,7 @@ from .skel import Model
 MAX_BODIES, MAX_SHAPES, MAX_GROUND, MAX_ACT = 24, 24, 4, 16
 
 OBS_Q1_DQ, OBS_HEIGHT_Q2_DQ = 0, 1
+TASK_LOCOMOTION, TASK_CARTPOLE, TASK_SWINGUP, TASK_DOUBLE_PENDULUM, TASK_REACHER2D = 0, 1, 2, 3, 4
 OPT_LCP_MODE, OPT_PGS_ITERS, OPT_FRICTION_ALL = 1, 2, 3
 LCP_EXACT, LCP_PGS = 0, 1
 
@@ -53,6 +54,7 @@ class CTask(C.Structure):
         ("dev_cost", C.c_double), ("zero_reward_on_blowup", C.c_int32),
         ("fluid_force", C.c_int32), ("fluid_offset", C.c_double), ("fluid_coef", C.c_double),
         ("reset_noise", C.c_double), ("state_bound", C.c_double),
+        ("kind", C.c_int32), ("reset_noise_dq", C.c_double), ("probe_body", C.c_int32 * 2), ("probe_local", (C.c_double * 3) * 2),
     ]
 
 
@@ -117,6 +119,10 @@ class Task:
     fluid_coef: float = 50.0
     reset_noise: float = 0.005
     state_bound: float = 100.0
+    kind: int = TASK_LOCOMOTION
+    reset_noise_dq: float = -1.0
+    probe_body: Sequence[int] = (-1, -1)
+    probe_local: Sequence[Sequence[float]] = ((0.0, 0.0, 0.0), (0.0, 0.0, 0.0))
 
     @property
     def n_act(self) -> int:
@@ -147,4 +153,9 @@ def pack_task(t: Task) -> CTask:
     ct.dev_cost, ct.zero_reward_on_blowup = t.dev_cost, int(t.zero_reward_on_blowup)
     ct.fluid_force, ct.fluid_offset, ct.fluid_coef = int(t.fluid_force), t.fluid_offset, t.fluid_coef
     ct.reset_noise, ct.state_bound = t.reset_noise, t.state_bound
+    ct.kind, ct.reset_noise_dq = int(t.kind), float(t.reset_noise_dq)
+    for k in range(2):
+        ct.probe_body[k] = int(t.probe_body[k])
+        for j in range(3):
+            ct.probe_local[k][j] = float(t.probe_local[k][j])
     return ct

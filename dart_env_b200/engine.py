@@ -102,6 +102,16 @@ class Engine:
         capi.check(fn(self.h, _ptr(q), _ptr(dq), self._stream()))
         return q, dq
 
+    def set_aux(self, aux: torch.Tensor):
+        """per-world task state [n, 3] float64 (the reacher's `self.target`, reacher2d.py:7,57-63)"""
+        self._chk(aux, (self.n, 3), torch.float64)
+        capi.check(self.L.dartb_set_aux(self.h, _ptr(aux), self._stream()))
+
+    def get_aux(self) -> torch.Tensor:
+        out = torch.empty((self.n, 3), dtype=torch.float64, device=self.device)
+        capi.check(self.L.dartb_get_aux(self.h, _ptr(out), self._stream()))
+        return out
+
     # --- stepping
     def reset(self, mask: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.n_obs == 0:  # physics-only handle: world.reset() only

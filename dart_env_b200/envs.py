@@ -40,8 +40,8 @@ def make(env_id: str, **kw) -> DartEnv:
     """gym.make(id): the env wrapped in TimeLimit(max_episode_steps) (registration.py:94-96);
     here the time limit runs inside the kernel (per-world elapsed counter)."""
     from .envs_contact_free import CONTACT_FREE
-    if env_id in CONTACT_FREE:  # host-side task layer; the TimeLimit cap is left to the caller
-        kw.pop("max_episode_steps", None)
+    if env_id in CONTACT_FREE:  # (gym/envs/__init__.py:219-264: the registered time limits)
+        kw.setdefault("max_episode_steps", CONTACT_FREE[env_id][1])
         return CONTACT_FREE[env_id][0](**kw)
     if env_id not in REGISTRY:
         raise KeyError("No registered env with id: %s (in scope: %s)" % (env_id, sorted(REGISTRY) + sorted(CONTACT_FREE)))

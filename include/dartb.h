@@ -98,7 +98,21 @@ typedef struct dartb_task {
     double  fluid_offset, fluid_coef; /* 0.05, 50.0 */
     double  reset_noise;           /* U(-noise, +noise) on q and dq (hopper.py:78-79) */
     double  state_bound;           /* 100: done if any |s[2:]| >= bound or non-finite */
+    /* the contact-free envs' step()/_get_obs()/reset_model(), selected by `kind` (0 = the
+     * locomotion layer parameterised above).  Actuators use act_dof / act_scale / act_lo / act_hi (+-inf = the
+     * reference does not clamp). */
+    int32_t kind;                  /* DARTB_TASK_* */
+    double  reset_noise_dq;        /* noise on dq when it differs from reset_noise (< 0: same) */
+    int32_t probe_body[2];         /* DOUBLE_PENDULUM: 'cart', 'weight' (to_world()[1], inverted_double_pendulum.py:28-31);
+                                      REACHER2D: [0] = bodynodes[-1] (com(), reacher2d.py:31) */
+    double  probe_local[2][3];     /* the body-local point of each probe (origin, or the local COM) */
 } dartb_task_t;
+
+enum { DARTB_TASK_LOCOMOTION = 0,      /* hopper / walker2d / half_cheetah / snake_7link */
+       DARTB_TASK_CARTPOLE = 1,        /* cart_pole.py:12-36: obs [q, dq], reward 1, done unless finite and |q1| <= 0.2 */
+       DARTB_TASK_SWINGUP = 2,         /* cartpole_swingup.py:14-52: reward 6 - |q1| - 0.01 a^2 - 0.01 |q0|; reset flips q1 by +-pi */
+       DARTB_TASK_DOUBLE_PENDULUM = 3, /* inverted_double_pendulum.py:19-63: obs [q0, sin, cos, dq]; randn velocity noise */
+       DARTB_TASK_REACHER2D = 4        /* reacher2d.py:17-64: per-world target (dartb_set_aux), reward -|tip - target| - a^2 */ };
 
 /* Options for dartb_set_option */
 enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
@@ -171,6 +185,12 @@ int dartb_step_host_gym(dartb_handle_t h, const float* h_action, float* obs_out,
  * origins d_fext [n, n_bodies, 3] (bn.add_ext_force, snake_7link.py:47), may be NULL. */
 int dartb_substep(dartb_handle_t h, const float* d_tau, const float* d_fext, void* stream);
 int dartb_substep_f64(dartb_handle_t h, const double* d_tau, const double* d_fext, void* stream);
+
+/* Per-world auxiliary task state, [n, 3] fp64 (converted to the engine precision inside): the reacher's target
+ * (`self.target`, reacher2d.py:7,57-63: world x, y, z).  Resets redraw it inside the kernel; these calls back the
+ * attribute for callers and tests.  Fails for task kinds without auxiliary state. */
+int dartb_set_aux(dartb_handle_t h, const double* d_aux, void* stream);
+int dartb_get_aux(dartb_handle_t h, double* d_aux, void* stream);
 
 /* world.collision_result.contacts of the LAST sub-step (walker2d.py:38-41).
  * d_count int32[n]; d_body int32[n, max_contacts] (robot body index per contact, -1 padded,

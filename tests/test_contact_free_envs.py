@@ -57,6 +57,59 @@ def test_loop_kernel_source_steps_contact_free_models(env_id):
     assert np.allclose(dq, g["step_dq2"], rtol=2e-4, atol=2e-4)
 
 
+def _env_cls(env_id):
+    from dart_env_b200.envs_contact_free import CONTACT_FREE
+    return CONTACT_FREE[env_id][0]
+
+
+@pytest.mark.parametrize("env_id", list(CASES))
+def test_fused_task_kinds_match_reference_classes(env_id):
+    """The CUDA task layer of the contact-free envs (csrc/task_kinds.cuh: obs / reward / done per dartb_task_t.kind),
+    compiled for the CPU by tools/host_emu, on the goldens' post-step states: the numbers the reference's own classes
+    returned.  fp64 instantiation: algorithmic equality; fp32: the stated tolerance."""
+    f, skel, dt, scale = CASES[env_id]
+    g = np.load(os.path.join(GOLD, f))
+    m = _model(skel, dt)
+    task = _env_cls(env_id)._task(None, m)
+    a2 = (g["step_action"] ** 2).sum(1)
+    for f64, tol in ((True, 1e-9), (False, 2e-5)):
+        obs, rew, done, *_ = emu.task_kind(m, task, g["step_q2"], g["step_dq2"], aux=g["step_target"], a2=a2, f64=f64)
+        assert np.allclose(obs, g["step_obs"], rtol=max(tol, 1e-6), atol=max(tol, 1e-6))     # obs are float32 at the boundary
+        assert np.allclose(rew, g["step_reward"], rtol=max(tol, 1e-9), atol=max(tol, 1e-9) * 10)
+        thr = {"DartCartPole-v1": np.abs(np.abs(g["step_q2"][:, 1]) - 0.2)}.get(env_id)
+        safe = np.ones(len(done), dtype=bool) if thr is None else thr > 1e-5
+        assert np.array_equal(done[safe], g["step_done"][safe].astype(bool))
+
+
+@pytest.mark.parametrize("env_id", list(CASES))
+def test_fused_reset_draws_follow_the_reference_distributions(env_id):
+    """reset_model() inside the kernel: counter-based draws with the reference's ranges (cart_pole.py:31-36,
+    cartpole_swingup.py:40-52, inverted_double_pendulum.py:56-63, reacher2d.py:50-64)."""
+    f, skel, dt, scale = CASES[env_id]
+    m = _model(skel, dt)
+    task = _env_cls(env_id)._task(None, m)
+    n, nd = 4000, m.n_dofs
+    obs, rew, done, q, dq, aux = emu.task_kind(m, task, np.zeros((n, nd)), np.zeros((n, nd)), f64=True, do_reset=True, seed=7)
+    q0, dq0 = np.array(m.q_init()), np.array(m.dq_init())
+    dqn = dq - dq0
+    if env_id == "DartCartPole-v1":
+        assert np.abs(q - q0).max() <= 0.01 and np.abs(dqn).max() <= 0.01 and (q - q0).std() > 0.005
+    elif env_id == "DartCartPoleSwingUp-v1":
+        flip = q[:, 1] - q0[1]
+        assert np.abs(np.abs(flip) - np.pi).max() <= 0.1 and 0.4 < (flip > 0).mean() < 0.6
+        assert np.abs(q[:, 0] - q0[0]).max() <= 0.1 and np.abs(dqn).max() <= 0.01
+    elif env_id == "DartDoubleInvertedPendulumEnv-v1":
+        assert np.abs(q - q0).max() <= 0.1
+        assert abs(dqn.std() - 0.1) < 0.005 and abs(dqn.mean()) < 0.005 and np.abs(dqn).max() > 0.3   # 0.1 * randn
+    else:
+        assert np.abs(q - q0).max() <= 0.01 and np.abs(dqn).max() <= 0.005
+        assert (aux[:, 1] == 0.01).all() and np.hypot(aux[:, 0], aux[:, 2]).max() < 0.2
+        assert np.abs(aux[:, [0, 2]]).max() > 0.15 and abs(aux[:, 0].mean()) < 0.01
+    # determinism: the same (seed, world, episode) key gives the same draw
+    _, _, _, q_b, dq_b, aux_b = emu.task_kind(m, task, np.zeros((n, nd)), np.zeros((n, nd)), f64=True, do_reset=True, seed=7)
+    assert np.array_equal(q, q_b) and np.array_equal(dq, dq_b) and np.array_equal(aux, aux_b)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("env_id", list(CASES))
 def test_batched_env_matches_reference_classes(env_id):
@@ -67,15 +120,18 @@ def test_batched_env_matches_reference_classes(env_id):
     g = np.load(os.path.join(GOLD, f))
     n = len(g["step_q"])
     env = make(env_id, num_envs=n, output="numpy", seed=0, auto_reset=False, f64=True)
-    assert "loop:generic" in env.engine.kernel_name
+    assert "loop:generic" in env.engine.kernel_name and env.fused     # ONE launch per step: the fused task layer
     env.set_state(g["step_q"], g["step_dq"])
     if env_id == "DartReacher-v1":
         env.target = torch.tensor(g["step_target"], device="cuda")
+    l0 = env.engine.launch_count
     ob, rew, done, _ = env.step(g["step_action"])
+    assert env.engine.launch_count - l0 == 1
     s = env.state_vector()
     nd = g["step_q"].shape[1]
-    assert np.allclose(s[:, :nd], g["step_q2"], rtol=1e-9, atol=1e-10)
-    assert np.allclose(ob, g["step_obs"], rtol=1e-8, atol=1e-8)
+    # (actions cross the boundary as float32: tau carries their 6e-8 relative rounding)
+    assert np.allclose(s[:, :nd], g["step_q2"], rtol=1e-7, atol=1e-8)
+    assert np.allclose(ob, g["step_obs"], rtol=1e-6, atol=1e-6)   # observations cross the boundary as float32
     assert np.allclose(rew, g["step_reward"], rtol=1e-8, atol=1e-8)
     assert np.array_equal(done, g["step_done"].astype(bool))
     env.close()

@@ -12,7 +12,7 @@ Tagged classes (the goldens carry the tags; nothing else is excluded):
            sits within MARGIN = 1e-4 of its threshold, so fp32 rounding may legitimately flip it;
   deep     a hand-built contact sweep state with a capsule more than DEEP = 0.03 m inside the ground (30x the
            velocity-correction cap): contact impulses amplify rounding through A^-1, cond(A) -> 1/CFM = 1e5.  These stay
-           bounded by TOL_SUB_DQ_DEEP = 2e-2 and keep their bit-exact contact sets.
+           bounded by TOL_SUB_DQ_DEEP = 2e-2 (q: 2e-4) and keep their bit-exact contact sets.
 Every test prints p50 / p99 / max of what it measured (pytest -s, and gpurun_out/parity_errors.log when writable).
 """
 import os
@@ -31,7 +31,7 @@ FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
 ENVS = list(SPECS)
 MARGIN = 1e-4
 DEEP = 0.03
-TOL_SUB_DQ, TOL_SUB_Q, TOL_SUB_DQ_DEEP = 2e-4, 1e-5, 2e-2
+TOL_SUB_DQ, TOL_SUB_Q, TOL_SUB_DQ_DEEP, TOL_SUB_Q_DEEP = 2e-4, 1e-5, 2e-2, 2e-4
 TOL_STEP_OBS, TOL_STEP_REW = 2e-4, 1e-3
 
 
@@ -135,12 +135,13 @@ def test_substep_fp32_within_stated_tolerance(models, env_id):
     ev = (np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"]))).max(1)
     deep = g["sub_contact_data"][:, :, 6].max(1) > DEEP
     _report("substep dq (not deep)", env_id, ev[safe & ~deep])
-    _report("substep q", env_id, eq[safe])
+    _report("substep q (not deep)", env_id, eq[safe & ~deep])
     assert ev[safe & ~deep].max() < TOL_SUB_DQ, ev[safe & ~deep].max()
-    assert eq[safe].max() < TOL_SUB_Q, eq[safe].max()
+    assert eq[safe & ~deep].max() < TOL_SUB_Q, eq[safe & ~deep].max()
     if (safe & deep).any():
         _report("substep dq (deep penetration)", env_id, ev[safe & deep])
         assert ev[safe & deep].max() < TOL_SUB_DQ_DEEP, ev[safe & deep].max()
+        assert eq[safe & deep].max() < TOL_SUB_Q_DEEP, eq[safe & deep].max()
 
 
 def _envstep(models, env_id, g, f64):

@@ -17,6 +17,7 @@ FILES = {"DartHopper-v1": "hopper.npz", "DartWalker2d-v1": "walker2d.npz",
          "DartHalfCheetah-v1": "halfcheetah.npz", "DartSnake7Link-v1": "snake7link.npz"}
 
 
+DEEP, TOL_SUB_DQ, TOL_SUB_Q, TOL_SUB_DQ_DEEP, TOL_SUB_Q_DEEP = 0.03, 2e-4, 1e-5, 2e-2, 2e-4   # == tests/test_gpu_parity.py (stated there)
 VARIANTS = [0, 1]  # 0 = unrolled per-topology kernel, 1 = loop / topology-generic kernel
 # (2 = lane-cooperative kernel: its own tests below, under the SIMT emulator of tools/host_emu/simt.h)
 
@@ -50,9 +51,12 @@ def test_kernel_source_fp32_within_tolerance(models, env_id, variant):
     safe = (g["sub_contact_margin"] > 1e-4) & (g["sub_limit_margin"] > 1e-4) & (g["sub_tie_margin"] > 1e-4)
     assert np.array_equal(cnt[safe], g["sub_ncontact"][safe])
     assert np.array_equal(body[safe], g["sub_contact_body"][safe])
-    ev = (np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"])))[safe].max(1)
-    eq = (np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"])))[safe].max(1)
-    assert np.median(ev) < 5e-6 and np.percentile(ev, 99) < 5e-4 and ev.max() < 5e-2 and eq.max() < 2e-4
+    ev = (np.abs(dq2 - g["sub_dq2"]) / (1 + np.abs(g["sub_dq2"]))).max(1)
+    eq = (np.abs(q2 - g["sub_q2"]) / (1 + np.abs(g["sub_q2"]))).max(1)
+    deep = g["sub_contact_data"][:, :, 6].max(1) > DEEP     # tagged class: capsule > 3 cm inside the ground
+    # the stated fp32 tolerances of tests/test_gpu_parity.py, as MAXIMA over the untagged samples
+    assert ev[safe & ~deep].max() < TOL_SUB_DQ and eq[safe & ~deep].max() < TOL_SUB_Q
+    assert not (safe & deep).any() or (ev[safe & deep].max() < TOL_SUB_DQ_DEEP and eq[safe & deep].max() < TOL_SUB_Q_DEEP)
 
 
 def test_kernel_source_pgs_equals_oracle_pgs(models):
@@ -150,9 +154,12 @@ def test_cooperative_kernel_fp32_within_tolerance(models, env_id):
     safe = (g["sub_contact_margin"][sel] > 1e-4) & (g["sub_limit_margin"][sel] > 1e-4) & (g["sub_tie_margin"][sel] > 1e-4)
     assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])
     assert np.array_equal(body[safe], g["sub_contact_body"][sel][safe])
-    ev = (np.abs(dq2 - g["sub_dq2"][sel]) / (1 + np.abs(g["sub_dq2"][sel])))[safe].max(1)
-    eq = (np.abs(q2 - g["sub_q2"][sel]) / (1 + np.abs(g["sub_q2"][sel])))[safe].max(1)
-    assert np.median(ev) < 2e-6 and np.percentile(ev, 99) < 5e-4 and ev.max() < 5e-2 and eq.max() < 2e-4
+    ev = (np.abs(dq2 - g["sub_dq2"][sel]) / (1 + np.abs(g["sub_dq2"][sel]))).max(1)
+    eq = (np.abs(q2 - g["sub_q2"][sel]) / (1 + np.abs(g["sub_q2"][sel]))).max(1)
+    deep = g["sub_contact_data"][sel][:, :, 6].max(1) > DEEP
+    assert np.median(ev[safe]) < 2e-6
+    assert ev[safe & ~deep].max() < TOL_SUB_DQ and eq[safe & ~deep].max() < TOL_SUB_Q
+    assert not (safe & deep).any() or (ev[safe & deep].max() < TOL_SUB_DQ_DEEP and eq[safe & deep].max() < TOL_SUB_Q_DEEP)
 
 
 def test_cooperative_kernel_world_independent_of_warp_neighbours(models):

@@ -58,3 +58,24 @@ def lcp(A, b, lo, hi, findex, mode=0, f64=True):
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     rc = L.emu_lcp(int(f64), n, dp(A), dp(b), dp(lo), dp(hi), fi.ctypes.data_as(C.POINTER(C.c_int32)), int(mode), dp(x))
     return x, rc
+
+
+def task_kind(model, task, q, dq, aux=None, a2=None, f64=True, do_reset=False, seed=0):
+    """obs / reward / done of the contact-free task kinds (csrc/task_kinds.cuh) for given post-step states; with
+    do_reset the states are first replaced by the kernel's reset_model() draws.  Returns (obs, reward, done, q, dq, aux)."""
+    L = lib()
+    cm, ct = pack_model(model), pack_task(task)
+    q = np.ascontiguousarray(q, dtype=np.float64).copy()
+    dq = np.ascontiguousarray(dq, dtype=np.float64).copy()
+    n = q.shape[0]
+    aux = np.zeros((n, 3)) if aux is None else np.ascontiguousarray(aux, dtype=np.float64).copy()
+    a2 = np.zeros(n) if a2 is None else np.ascontiguousarray(a2, dtype=np.float64)
+    obs = np.zeros((n, task.n_obs), dtype=np.float32)
+    rew = np.zeros(n)
+    done = np.zeros(n, dtype=np.int32)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = L.emu_task_kind(C.byref(cm), C.byref(ct), int(f64), n, dp(q), dp(dq), dp(aux), dp(a2), int(do_reset), C.c_uint64(seed),
+                         obs.ctypes.data_as(C.POINTER(C.c_float)), dp(rew), done.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise RuntimeError(L.emu_last_error().decode())
+    return obs, rew, done.astype(bool), q, dq, aux

@@ -10,6 +10,7 @@
 #include "../../dart_env_b200/csrc/planar_loop.cuh"
 #include "simt.h"
 #include "../../dart_env_b200/csrc/planar_coop.cuh"
+#include "../../dart_env_b200/csrc/task_kinds.cuh"
 
 template <class T, typename R>
 static void run_substep(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
@@ -134,6 +135,42 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
     RUN(TopoHopper) RUN(TopoWalker) RUN(TopoCheetah) RUN(TopoSnake)
     g_err = "no topology for " + res.signature;
     return 1;
+}
+
+// task layer of the contact-free kinds (task_kinds.cuh) on ONE state per world: obs [n, n_obs], reward [n], done [n];
+// with do_reset != 0 the state is first replaced by reset_model()'s draw (q, dq, aux are in/out then)
+template <typename R>
+static void run_task_kind(const PModel<R>& M, const PTask<R>& K, int n, double* q, double* dq, double* aux, const double* a2,
+                          int do_reset, uint64_t seed, float* obs, double* rew, int32_t* done) {
+    const int nb = M.nb;
+    for (int w = 0; w < n; w++) {
+        R qq[LOOP_MAXB], dd[LOOP_MAXB], tg[3];
+        for (int i = 0; i < nb; i++) { qq[i] = (R)q[w * nb + i]; dd[i] = (R)dq[w * nb + i]; }
+        for (int c = 0; c < 3; c++) tg[c] = (R)aux[w * 3 + c];
+        if (do_reset) {
+            reset_state_kind<R>(M, K, seed, w, 0, qq, dd, tg);
+            for (int i = 0; i < nb; i++) { q[w * nb + i] = (double)qq[i]; dq[w * nb + i] = (double)dd[i]; }
+            for (int c = 0; c < 3; c++) aux[w * 3 + c] = (double)tg[c];
+        }
+        R r; bool d;
+        task_kind_eval<R>(M, K, qq, dd, tg, (R)a2[w], r, d);
+        write_obs_kind<R>(M, K, qq, dd, tg, obs + (size_t)w * K.n_obs);
+        rew[w] = (double)r; done[w] = d ? 1 : 0;
+    }
+}
+extern "C" int emu_task_kind(const dartb_model_t* model, const dartb_task_t* task, int f64, int n, double* q, double* dq,
+                             double* aux, const double* a2, int do_reset, uint64_t seed, float* obs, double* rew, int32_t* done) {
+    lower::Result res;
+    std::string why = lower::lower_model(*model, *task, res);
+    if (!why.empty()) { g_err = why; return 1; }
+    if (res.t.kind == DARTB_TASK_LOCOMOTION) { g_err = "not a contact-free task kind"; return 1; }
+    if (f64) run_task_kind<double>(res.m, res.t, n, q, dq, aux, a2, do_reset, seed, obs, rew, done);
+    else {
+        PModel<float> mf; PTask<float> tf;
+        lower::convert(res.m, mf); lower::convert(res.t, tf);
+        run_task_kind<float>(mf, tf, n, q, dq, aux, a2, do_reset, seed, obs, rew, done);
+    }
+    return 0;
 }
 
 extern "C" float emu_reset_uniform(uint64_t seed, int64_t world, uint32_t episode, int i) {
