@@ -15,7 +15,7 @@ _EXPORTS = [
     "dartb_get_state", "dartb_set_state_f64", "dartb_get_state_f64", "dartb_step", "dartb_substep",
     "dartb_substep_f64", "dartb_get_contacts", "dartb_get_truncated", "dartb_max_contacts", "dartb_num_worlds",
     "dartb_num_dofs", "dartb_is_f64", "dartb_launch_count", "dartb_kernel_name", "dartb_last_error",
-    "dartb_version", "dartb_describe", "dartb_step_host", "dartb_step_host_gym", "dartb_seed", "dartb_set_aux", "dartb_get_aux",
+    "dartb_version", "dartb_describe", "dartb_step_host", "dartb_step_host_gym", "dartb_seed", "dartb_seed_worlds", "dartb_register_host", "dartb_unregister_host", "dartb_set_aux", "dartb_get_aux",
 ]
 
 
@@ -50,6 +50,9 @@ def load(build_if_missing: bool = True):
         "dartb_destroy": (C.c_int, [vp]),
         "dartb_set_option": (C.c_int, [vp, i32, dbl]),
         "dartb_seed": (C.c_int, [vp, u64]),
+        "dartb_seed_worlds": (C.c_int, [vp, vp]),
+        "dartb_register_host": (C.c_int, [vp, vp, C.c_size_t]),
+        "dartb_unregister_host": (C.c_int, [vp, vp]),
         "dartb_set_aux": (C.c_int, [vp, vp, vp]),
         "dartb_get_aux": (C.c_int, [vp, vp, vp]),
         "dartb_reset": (C.c_int, [vp, vp, vp, vp]),

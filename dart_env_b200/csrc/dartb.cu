@@ -71,6 +71,7 @@ struct dartb_engine {
     PTask<float> tf; PTask<double> td;
     dartb_model_t model; dartb_task_t task;   // kept so friction/options can re-lower
     void* q = nullptr; void* dq = nullptr;
+    uint64_t* seeds = nullptr;                // [n] per-world seeds (dartb_seed_worlds) or null
     void* aux = nullptr;                      // [3][n] of Real: per-world task state (reacher target), or null
     void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
@@ -88,6 +89,8 @@ struct dartb_engine {
     // host-facing step (dartb_step_host): pinned staging + device mirrors, one stream
     float* h_stage = nullptr; float* d_stage = nullptr; float* h_stage_dev = nullptr; size_t stage_floats = 0;
     const void* zc_h[3] = {nullptr, nullptr, nullptr}; void* zc_d[3] = {nullptr, nullptr, nullptr};   // zero-copy output aliases
+    struct HostRange { const char* h; size_t bytes; char* d; };
+    std::vector<HostRange> host_ranges;       // dartb_register_host: page-locked ranges whose device alias is known
     std::string kernel_name;
 };
 
@@ -191,7 +194,7 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.hint = e->hint;
     a.aux = (R*)e->aux;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
-    a.seed = e->seed; a.world_offset = e->world_offset;
+    a.seed = e->seed; a.world_offset = e->world_offset; a.seeds = e->seeds;
     if (e->contacts) { a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; }
     a.sink.maxc = e->max_contacts;
     return a;
@@ -399,7 +402,7 @@ int dartb_create_f64(const dartb_model_t* model, const dartb_task_t* task, int32
 int dartb_destroy(dartb_handle_t e) {
     if (!e) return 0;
     DeviceGuard g(e->device);
-    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->aux); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
+    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->aux); cudaFree(e->seeds); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
     cudaFree(e->truncated); cudaFree(e->hint); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
     if (e->coop_tab) cudaFree(e->coop_tab);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -448,6 +451,18 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
 int dartb_seed(dartb_handle_t e, uint64_t seed) {
     if (!e) return fail("null handle");
     e->seed = seed;   // a kernel argument: takes effect with the next launch, no synchronisation
+    if (e->seeds) {   // back to one key for the whole batch
+        DeviceGuard g(e->device);
+        CK(cudaDeviceSynchronize());
+        cudaFree(e->seeds); e->seeds = nullptr;
+    }
+    return 0;
+}
+int dartb_seed_worlds(dartb_handle_t e, const uint64_t* h_seeds) {
+    if (!e || !h_seeds) return fail("null argument");
+    DeviceGuard g(e->device);
+    if (!e->seeds) CK(cudaMalloc((void**)&e->seeds, 8 * (size_t)e->n));
+    CK(cudaMemcpy(e->seeds, h_seeds, 8 * (size_t)e->n, cudaMemcpyHostToDevice));   // synchronous: seeding is not a hot path
     return 0;
 }
 
@@ -491,7 +506,8 @@ int dartb_step(dartb_handle_t e, const float* d_action, float* d_obs, float* d_r
 }
 
 // device-visible alias of a page-locked host pointer (UVA: normally the same value), or null if the
-// memory is pageable
+// memory is pageable.  Queries the driver: several microseconds per call (measured: five of them per step cost
+// more than the step kernel), so the per-step paths look registered ranges up first (dartb_register_host).
 static void* mapped_alias(const void* h) {
     cudaPointerAttributes pa;
     void* d = nullptr;
@@ -500,6 +516,13 @@ static void* mapped_alias(const void* h) {
         return d;
     cudaGetLastError();  // a pageable pointer may leave cudaErrorInvalidValue behind on old drivers
     return nullptr;
+}
+
+static void* alias_of(const dartb_engine* e, const void* h) {
+    const char* p = (const char*)h;
+    for (const auto& r : e->host_ranges)
+        if (p >= r.h && p < r.h + r.bytes) return r.d + (p - r.h);
+    return mapped_alias(h);
 }
 
 // the pinned (host-mapped) staging block of the host-facing step and its device mirror
@@ -515,6 +538,22 @@ static int ensure_stage(dartb_engine* e, size_t need) {
     cudaGetLastError();
     e->stage_floats = need;
     return 0;
+}
+
+int dartb_register_host(dartb_handle_t e, const void* h_ptr, size_t bytes) {
+    if (!e || !h_ptr || !bytes) return fail("null argument");
+    DeviceGuard g(e->device);
+    void* d = mapped_alias(h_ptr);
+    if (!d) return fail("dartb_register_host: the range is not page-locked, device-mapped host memory");
+    for (auto& r : e->host_ranges) if (r.h == (const char*)h_ptr) { r.bytes = bytes; r.d = (char*)d; return 0; }
+    e->host_ranges.push_back({(const char*)h_ptr, bytes, (char*)d});
+    return 0;
+}
+int dartb_unregister_host(dartb_handle_t e, const void* h_ptr) {
+    if (!e) return fail("null handle");
+    for (size_t i = 0; i < e->host_ranges.size(); i++)
+        if (e->host_ranges[i].h == (const char*)h_ptr) { e->host_ranges.erase(e->host_ranges.begin() + i); return 0; }
+    return fail("dartb_unregister_host: unknown range");
 }
 
 int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done,
@@ -534,12 +573,12 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
         // host memory over PCIe itself (coalesced 128 B lines through its shared-memory staging), so the
         // whole host step is ONE launch + ONE sync: no memcpy nodes (each costs ~5 us of latency, more than
         // moving these ~250 KB does).  Pageable caller buffers go through the pinned staging block.
-        const float* a_dev = (const float*)mapped_alias(h_action);
+        const float* a_dev = (const float*)alias_of(e, h_action);
         if (!a_dev) { std::memcpy(e->h_stage, h_action, fa * 4); a_dev = e->h_stage_dev; }
         // (the caller's output buffers are normally the same page-locked arrays every step: look them up once)
         if (h_obs != e->zc_h[0] || h_reward != e->zc_h[1] || h_done != e->zc_h[2]) {
             e->zc_h[0] = h_obs; e->zc_h[1] = h_reward; e->zc_h[2] = h_done;
-            e->zc_d[0] = mapped_alias(h_obs); e->zc_d[1] = mapped_alias(h_reward); e->zc_d[2] = mapped_alias(h_done);
+            e->zc_d[0] = alias_of(e, h_obs); e->zc_d[1] = alias_of(e, h_reward); e->zc_d[2] = alias_of(e, h_done);
         }
         float* o_dev = (float*)e->zc_d[0];
         float* r_dev = (float*)e->zc_d[1];
@@ -567,7 +606,7 @@ int dartb_step_host(dartb_handle_t e, const float* h_action, float* h_obs, float
     if (rc) return rc;
     // results: DMA straight into the caller's buffers when they are page-locked (the DartEnv wrapper
     // allocates its output arrays pinned), else one D2H into the pinned staging block + memcpy
-    const bool direct = mapped_alias(h_obs) && mapped_alias(h_reward) && mapped_alias(h_done);
+    const bool direct = alias_of(e, h_obs) && alias_of(e, h_reward) && alias_of(e, h_done);
     if (direct) {
         CK(cudaMemcpyAsync(h_obs, d_obs, fo * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_reward, d_rew, fr * 4, cudaMemcpyDeviceToHost, st));
@@ -597,12 +636,12 @@ int dartb_step_host_gym(dartb_handle_t e, const float* h_action, float* obs_out,
         // Page-locked outputs (the DartEnv wrapper hands out arrays of its pinned pool): the kernel itself writes the
         // reference's return types (float32 obs, float64 rewards, bool dones / truncated flags) over PCIe: ONE launch
         // and ONE sync per env.step(), no conversion pass, no memcpy.
-        float* o_dev = (float*)mapped_alias(obs_out);
-        double* r_dev = (double*)mapped_alias(reward_out);
-        uint8_t* d_dev = (uint8_t*)mapped_alias(done_out);
-        uint8_t* t_dev = truncated_out ? (uint8_t*)mapped_alias(truncated_out) : nullptr;
+        float* o_dev = (float*)alias_of(e, obs_out);
+        double* r_dev = (double*)alias_of(e, reward_out);
+        uint8_t* d_dev = (uint8_t*)alias_of(e, done_out);
+        uint8_t* t_dev = truncated_out ? (uint8_t*)alias_of(e, truncated_out) : nullptr;
         if (o_dev && r_dev && d_dev && (t_dev || !truncated_out)) {
-            const float* a_dev = (const float*)mapped_alias(h_action);
+            const float* a_dev = (const float*)alias_of(e, h_action);
             if (!a_dev) { std::memcpy(e->h_stage, h_action, fa * 4); a_dev = e->h_stage_dev; }
             int rc = e->f64 ? launch_step<double>(e, a_dev, o_dev, nullptr, d_dev, auto_reset, st, r_dev, t_dev)
                             : launch_step<float>(e, a_dev, o_dev, nullptr, d_dev, auto_reset, st, r_dev, t_dev);

@@ -164,7 +164,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     }
     if (active && done && a.auto_reset) {
         const uint32_t ep = a.episode[w];
-        reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        reset_state<T, R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq);
         a.episode[w] = ep + 1;
         hint = ~(uint64_t)0;
     }
@@ -208,7 +208,7 @@ k_reset(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K,
     });
     if (doit) {
         const uint32_t ep = a.episode[w];
-        reset_state<T, R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        reset_state<T, R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq);
         a.episode[w] = ep + 1;
         a.elapsed[w] = 0;
         a.hint[w] = ~(uint64_t)0;
@@ -354,7 +354,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
         }
         if (active && done && a.auto_reset) {
             const uint32_t ep = a.episode[w];
-            reset_state_kind<R>(M, K, a.seed, a.world_offset + w, ep, q, dq, tg);
+            reset_state_kind<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq, tg);
             a.episode[w] = ep + 1;
             if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
         }
@@ -401,7 +401,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     }
     if (active && done && a.auto_reset) {
         const uint32_t ep = a.episode[w];
-        reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        reset_state_loop<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq);
         a.episode[w] = ep + 1;
     }
     if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
@@ -438,9 +438,9 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
     if (a.aux && active) { tg[0] = a.aux[w]; tg[1] = a.aux[(size_t)a.n + w]; tg[2] = a.aux[2 * (size_t)a.n + w]; }
     if (doit) {
         const uint32_t ep = a.episode[w];
-        if (K.kind == DARTB_TASK_LOCOMOTION) reset_state_loop<R>(M, K, a.seed, a.world_offset + w, ep, q, dq);
+        if (K.kind == DARTB_TASK_LOCOMOTION) reset_state_loop<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq);
         else {
-            reset_state_kind<R>(M, K, a.seed, a.world_offset + w, ep, q, dq, tg);
+            reset_state_kind<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq, tg);
             if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
         }
         a.episode[w] = ep + 1;

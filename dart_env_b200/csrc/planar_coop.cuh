@@ -1078,8 +1078,8 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     if (do_reset) {
         if (c.isb) {   // reset_model(): q0 + U(+-noise), dq0 + U(+-noise), fp32 arithmetic (bit-identical to the oracle)
             const float noise = (float)K.reset_noise;
-            const float ua = __fmul_rn(reset_uniform(a.seed, a.world_offset + w, ep, l), noise);
-            const float ub = __fmul_rn(reset_uniform(a.seed, a.world_offset + w, ep, NB + l), noise);
+            const float ua = __fmul_rn(reset_uniform(reset_seed(a, w), reset_world(a, w), ep, l), noise);
+            const float ub = __fmul_rn(reset_uniform(reset_seed(a, w), reset_world(a, w), ep, NB + l), noise);
             q = (R)__fadd_rn((float)c.qinit, ua);
             dq = (R)__fadd_rn((float)c.dqinit, ub);
         }

@@ -1039,8 +1039,15 @@ struct StepArgs {
     int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for
     uint64_t seed;
     int64_t world_offset;
+    const uint64_t* seeds;   // [n] per-world seeds (VectorEnv.seed(list), sync_vector_env.py:50-57) or null
     ContactSink<R> sink;
 };
+// Philox key of world w's reset draws: (seed, global world id), or (its own seed, 0) after a per-world seeding, so that
+// world i seeded s_i draws what a single env seeded s_i draws
+template <typename R>
+DEVI uint64_t reset_seed(const StepArgs<R>& a, int w) { return a.seeds ? a.seeds[w] : a.seed; }
+template <typename R>
+DEVI int64_t reset_world(const StepArgs<R>& a, int w) { return a.seeds ? (int64_t)0 : a.world_offset + w; }
 
 // ------------------------------------------------------------------------ kinematics only
 // positions/orientations for the task layer (height of a body COM)

@@ -37,7 +37,9 @@ class _PinnedOutPool:
     pool that nobody references any more (CPython refcounts: any array or view the caller still holds keeps its slot
     out of circulation).  No np.empty, no memcpy, no conversion pass per step."""
 
-    def __init__(self, n: int, n_obs: int, with_trunc: bool, max_slots: int = 64):
+    def __init__(self, engine, n: int, n_obs: int, with_trunc: bool, max_slots: int = 64, alloc=None):
+        self.engine = engine
+        self._alloc = alloc or self._alloc_pinned
         self.n, self.n_obs, self.with_trunc, self.max_slots = n, n_obs, with_trunc, max_slots
         a16 = lambda v: (v + 15) // 16 * 16
         self.off_rew = a16(n * n_obs * 4)
@@ -47,21 +49,27 @@ class _PinnedOutPool:
         self.slots = []
         self._next = 0
 
+    def _alloc_pinned(self, nbytes):
+        """page-locked block registered with the handle (zero-copy without per-step driver queries)"""
+        t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        capi.check(self.engine.L.dartb_register_host(self.engine.h, C.c_void_p(t.data_ptr()), nbytes))
+        return t, t.data_ptr()
+
     def _new_slot(self):
-        t = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
-        base = (C.c_char * self.nbytes).from_address(t.data_ptr())
+        t, p = self._alloc(self.nbytes)
+        base = (C.c_char * self.nbytes).from_address(p)
         n, no = self.n, self.n_obs
         obs1 = np.frombuffer(base, dtype=np.float32, count=n * no, offset=0)
         obs = obs1.reshape(n, no)
         rew = np.frombuffer(base, dtype=np.float64, count=n, offset=self.off_rew)
         done = np.frombuffer(base, dtype=np.bool_, count=n, offset=self.off_done)
         trunc = np.frombuffer(base, dtype=np.bool_, count=n, offset=self.off_trunc) if self.with_trunc else None
-        p = t.data_ptr()
         ptrs = (C.c_void_p(p), C.c_void_p(p + self.off_rew), C.c_void_p(p + self.off_done),
                 C.c_void_p(p + self.off_trunc) if self.with_trunc else None)
-        watched = [a for a in (obs1, obs, rew, done, trunc) if a is not None]
-        slot = {"keep": (t, base), "obs": obs, "rew": rew, "done": done, "trunc": trunc, "ptrs": ptrs, "watched": watched}
-        slot["idle"] = [sys.getrefcount(a) for a in watched]
+        slot = {"keep": (t, base), "obs": obs, "rew": rew, "done": done, "trunc": trunc, "ptrs": ptrs,
+                "watched": [a for a in (obs1, obs, rew, done, trunc) if a is not None]}
+        del obs1, obs, rew, done, trunc   # the idle refcounts must not include this frame's locals
+        slot["idle"] = [sys.getrefcount(a) for a in slot["watched"]]
         self.slots.append(slot)
         return slot
 
@@ -178,7 +186,10 @@ class DartEnv:
         self._n_obs = torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory().numpy()
         self._n_rew = torch.empty((n,), dtype=torch.float32).pin_memory().numpy()
         self._n_done = torch.empty((n,), dtype=torch.uint8).pin_memory().numpy()
-        self._c_obs, self._c_rew, self._c_done = (C.c_void_p(x.ctypes.data) for x in (self._n_obs, self._n_rew, self._n_done))
+        self._n_act = torch.empty((n, self.act_dim), dtype=torch.float32).pin_memory().numpy()
+        self._c_obs, self._c_rew, self._c_done, self._c_act = (C.c_void_p(x.ctypes.data) for x in (self._n_obs, self._n_rew, self._n_done, self._n_act))
+        for x in (self._n_obs, self._n_rew, self._n_done, self._n_act):   # zero-copy without per-step driver queries
+            capi.check(self.engine.L.dartb_register_host(self.engine.h, C.c_void_p(x.ctypes.data), x.nbytes))
         self._pool = None   # pinned output slots of the batched host path (built on first use)
 
     @property
@@ -194,6 +205,14 @@ class DartEnv:
     def seed(self, seed=None):
         """dart_env.py:117-119.  Reset noise comes from a counter-based generator keyed by
         (seed, global world id, episode), so results do not depend on sharding."""
+        if isinstance(seed, (list, tuple, np.ndarray)):
+            # VectorEnv.seed([s_0, ...]) (gym/vector/sync_vector_env.py:50-57): world i draws what a single env seeded s_i draws
+            seeds = np.ascontiguousarray([int(s) & 0xFFFFFFFFFFFFFFFF for s in seed], dtype=np.uint64)
+            if seeds.shape != (self.num_envs,):
+                raise ValueError("seed list must have one entry per env")
+            self.seed(int(seeds[0]))
+            capi.check(self.engine.L.dartb_seed_worlds(self.engine.h, seeds.ctypes.data))
+            return [int(s) for s in seeds]
         if seed is None:
             seed = int.from_bytes(os.urandom(4), "little")
         self._seed_value = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -299,20 +318,19 @@ class DartEnv:
             act = a.reshape(self.num_envs, self.act_dim).to(torch.float32).contiguous()
             self.engine.step(act, self._obs, self._rew, self._done, self.auto_reset)
         else:
-            # host path: one library call does pinned H2D, the launch, one D2H and the sync
-            act = a
-            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == (self.num_envs, self.act_dim)
-                    and a.flags.c_contiguous):
-                act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim))
+            # host path: ONE library call (launch + sync); the kernel reads the actions from, and writes the results to,
+            # page-locked host memory that is registered with the handle
+            np.copyto(self._n_act, np.asarray(a).reshape(self.num_envs, self.act_dim), casting="same_kind")
+            act_ptr = self._c_act
             eng = self.engine
             if self.batched and self.copy:
                 # reference return types in one library call, written by the kernel into an unreferenced pinned slot
                 if self._pool is None or self._pool.with_trunc != bool(self._max_episode_steps):
-                    self._pool = _PinnedOutPool(self.num_envs, self.obs_dim, bool(self._max_episode_steps))
+                    self._pool = _PinnedOutPool(eng, self.num_envs, self.obs_dim, bool(self._max_episode_steps))
                 slot = self._pool.take()
                 if slot is not None:
                     po, pr, pd, pt = slot["ptrs"]
-                    rc = eng.L.dartb_step_host_gym(eng.h, act.ctypes.data, po, pr, pd, pt, int(self.auto_reset), eng._stream())
+                    rc = eng.L.dartb_step_host_gym(eng.h, act_ptr, po, pr, pd, pt, int(self.auto_reset), eng._stream())
                     if rc:
                         capi.check(rc)
                     return slot["obs"], slot["rew"], slot["done"], ({"TimeLimit.truncated": slot["trunc"]} if pt is not None else {})
@@ -322,14 +340,14 @@ class DartEnv:
                 rew = np.empty((n,), dtype=np.float64)
                 done = np.empty((n,), dtype=np.bool_)
                 trunc = np.empty((n,), dtype=np.bool_) if self._max_episode_steps else None
-                rc = eng.L.dartb_step_host_gym(eng.h, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                rc = eng.L.dartb_step_host_gym(eng.h, act_ptr, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
                                                trunc.ctypes.data if trunc is not None else None, int(self.auto_reset),
                                                eng._stream())
                 if rc:
                     capi.check(rc)
                 return obs, rew, done, ({"TimeLimit.truncated": trunc} if trunc is not None else {})
             # (the output arrays are this env's own page-locked buffers: their pointers are cached)
-            rc = eng.L.dartb_step_host(eng.h, act.ctypes.data, self._c_obs, self._c_rew, self._c_done, int(self.auto_reset),
+            rc = eng.L.dartb_step_host(eng.h, act_ptr, self._c_obs, self._c_rew, self._c_done, int(self.auto_reset),
                                        eng._stream())
             if rc:
                 capi.check(rc)

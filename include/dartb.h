@@ -142,6 +142,9 @@ int dartb_set_option(dartb_handle_t h, int32_t key, double value);
  * world id and episode counter).  Like the reference it touches nothing else: physics state, episode counters
  * and options stay as they are. */
 int dartb_seed(dartb_handle_t h, uint64_t seed);
+/* VectorEnv.seed([s_0, ..., s_{n-1}]) (gym/vector/sync_vector_env.py:50-57): world i draws what a single env seeded
+ * s_i draws.  h_seeds is a HOST array of n_worlds values; synchronous. */
+int dartb_seed_worlds(dartb_handle_t h, const uint64_t* h_seeds);
 
 /* world.reset() + reset_model(): q0 + U(+-noise), dq0 + U(+-noise), returns obs.
  * d_mask: uint8[n] (NULL = all worlds). d_obs may be NULL.  (dart_world.py:20-22, hopper.py:76-84) */
@@ -171,6 +174,13 @@ int dartb_step(dartb_handle_t h, const float* d_action, float* d_obs, float* d_r
  * a DartEnv user makes per step (bench.py "e2e"). */
 int dartb_step_host(dartb_handle_t h, const float* h_action, float* h_obs, float* h_reward,
                     uint8_t* h_done, int32_t auto_reset, void* stream);
+
+/* Tell the handle that [h_ptr, h_ptr + bytes) is page-locked, device-mapped host memory (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) that stays so until it is unregistered or the handle is destroyed.
+ * dartb_step_host / dartb_step_host_gym then use pointers inside it zero-copy WITHOUT asking the driver on
+ * every step (cudaPointerGetAttributes costs microseconds: several per step exceed the step kernel). */
+int dartb_register_host(dartb_handle_t h, const void* h_ptr, size_t bytes);
+int dartb_unregister_host(dartb_handle_t h, const void* h_ptr);
 
 /* The same step with the reference's vectorised RETURN TYPES (gym/vector/sync_vector_env.py:44-47,73-84):
  * obs_out float32 [n, n_obs] (a fresh copy: VectorEnv(copy=True)), reward_out float64 [n], done_out bool [n]

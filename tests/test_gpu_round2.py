@@ -148,12 +148,12 @@ def test_every_host_buffer_route_equals_the_device_path():
 
 def test_zerocopy_off_copy_path_equals_the_device_path():
     """DARTB_ZEROCOPY=0 (explicit H2D / D2H copies) is read once per process: run it in a child."""
-    code = ("import sys; sys.path.insert(0, %r); import numpy as np; from tests.test_gpu_round2 import _host_step_outputs as f\n"
+    code = ("import sys; sys.path[:0] = [%r, %r]; import numpy as np; from test_gpu_round2 import _host_step_outputs as f\n"
             "ref = f('DartHopper-v1', 300, 6, 'device')\n"
             "for route in ('pinned', 'pageable', 'gym_pageable'):\n"
             "    o, r, d = f('DartHopper-v1', 300, 6, route)\n"
             "    assert np.array_equal(o, ref[0]) and np.array_equal(r, ref[1]) and np.array_equal(d, ref[2]), route\n"
-            "print('copy-path ok')\n") % ROOT
+            "print('copy-path ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
     env = dict(os.environ, DARTB_ZEROCOPY="0")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "copy-path ok" in res.stdout, res.stdout + res.stderr
@@ -200,7 +200,7 @@ def test_full_constraint_set_no_row_dropped(env_id, variant):
     cand.sort(key=lambda c: -c[0])
     S = [(c[2], c[3], c[4], c[0], c[5]) for c in cand[:8]]
     print("%s: largest row counts found %s of NR = %d" % (env_id, [c[0] for c in cand[:8]], NR))
-    assert S[0][3] >= NR - (6 if env_id == "DartHalfCheetah-v1" else 0)   # hopper, walker: the FULL set, 2*NS + NL rows
+    assert S[0][3] >= NR - (8 if env_id == "DartHalfCheetah-v1" else 0)   # hopper, walker: the FULL set, 2*NS + NL rows
     q, dq, ref = (np.array([s[k] for s in S]) for k in range(3))
     nrows = max(s[3] for s in S)
     eng = Engine(m, spec.task, len(S), f64=True, kernel_variant=variant)

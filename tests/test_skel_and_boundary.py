@@ -199,3 +199,44 @@ def test_spaces_and_specs():
     hi = np.inf * np.ones(11)
     o = Box(-hi, hi)
     assert np.zeros(11) in o and o.sample().shape == (11,)
+
+
+def test_output_pool_hands_out_only_unreferenced_slots():
+    """VectorEnv(copy=True) semantics of the batched host path without copies (dart_env._PinnedOutPool): a slot is
+    reused only when the caller holds no array or view of it.  (Host logic: plain memory stands in for pinned memory.)"""
+    import ctypes as C
+
+    from dart_env_b200.dart_env import _PinnedOutPool
+    blocks = []
+
+    def alloc(nbytes):
+        buf = (C.c_char * nbytes)()
+        blocks.append(buf)
+        return buf, C.addressof(buf)
+
+    pool = _PinnedOutPool(None, 16, 5, True, max_slots=4, alloc=alloc)
+    s = pool.take()
+    o, r, d, t = s["obs"], s["rew"], s["done"], s["trunc"]
+    assert o.shape == (16, 5) and o.dtype == np.float32 and r.dtype == np.float64 and d.dtype == np.bool_ and t.dtype == np.bool_
+    o[:] = 1.0
+    del s
+    s2 = pool.take()                      # `o` is still held: a different slot
+    assert s2["obs"] is not o and len(pool.slots) == 2
+    s2["obs"][:] = 2.0
+    assert (o == 1.0).all()
+    del s2
+    view = o[3]                           # a VIEW keeps the slot out of circulation
+    del o, r, d, t
+    for _ in range(10):
+        s3 = pool.take()
+        assert s3["obs"].base is not view.base
+        s3["obs"][:] = 3.0
+        del s3
+    assert (view == 1.0).all() and len(pool.slots) == 2
+    del view
+    seen = set()
+    for _ in range(4):
+        s4 = pool.take(); seen.add(id(s4)); del s4
+    assert len(seen) == 2 and len(pool.slots) == 2    # both slots circulate again
+    held = [pool.take()["obs"] for _ in range(4)]
+    assert len({id(h) for h in held}) == 4 and pool.take() is None    # max_slots all held: caller falls back to copies
