@@ -1008,6 +1008,58 @@ DEVI void lcp_pgs(int n, const R* A, R* x, const R* b, const R* lo, const R* hi,
         }
 }
 
+// The same sweeps with the whole problem in REGISTERS for n <= NM (fully unrolled rows, rolled sweep loop whose body
+// stays in the L0 instruction cache).  r2 measurement (gpurun_out/r2a_sweep.log): the thread-local form above made the
+// PGS path SLOWER than the exact solver (Walker2d 16384 worlds: 390 vs 165 us per env step; every A[i*n+j] is a
+// dependent L1 round trip for a lone warp).  Same iterates as lcp_pgs up to the rounding of s * (1 / a_ii) vs s / a_ii.
+template <typename R, int NM>
+DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg, int iters) {
+    R A[NM][NM], b[NM], lo[NM], hi[NM], x[NM], inv[NM];
+    int fi[NM];
+#pragma unroll
+    for (int i = 0; i < NM; i++) {
+        const bool on = i < n;
+        b[i] = on ? bg[i] : (R)0; lo[i] = on ? log_[i] : (R)0; hi[i] = on ? hig[i] : (R)0; fi[i] = on ? fidxg[i] : -1;
+        x[i] = 0;
+        R aii = 0;
+#pragma unroll
+        for (int j = 0; j < NM; j++) { A[i][j] = (on && j < n) ? Ag[i * n + j] : (R)0; if (j == i) aii = A[i][j]; }
+        inv[i] = (on && !(aii < (R)1e-9)) ? (R)1 / aii : (R)0;     // 0: the row keeps x = 0 (lcp_pgs: aii < 1e-9)
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NM; i++) {
+            R s = b[i];
+#pragma unroll
+            for (int j = 0; j < NM; j++) if (j != i) s -= A[i][j] * x[j];
+            s *= inv[i];
+            R l = lo[i], h = hi[i];
+            if (fi[i] >= 0) {
+                R xn = 0;
+#pragma unroll
+                for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
+                h = hi[i] * xn; l = -h;
+            }
+            s = s > h ? h : s;
+            s = s < l ? l : s;
+            x[i] = inv[i] != 0 ? s : (R)0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NM; i++) if (i < n) xg[i] = x[i];
+}
+// PGS dispatch: the register form per WARP size class (one code path per warp), thread-local sweeps above 8 rows
+template <typename R, int NR>
+DEVI void lcp_pgs_dispatch(int n, const R* A, R* x, const R* b, const R* lo, const R* hi, const int* fidx, int iters) {
+    const int nmax = warp_max_active(n);
+    if (nmax <= 4) { pgs_small<R, 4>(n, A, x, b, lo, hi, fidx, iters); return; }
+    if constexpr (NR > 4) {
+        if (nmax <= 8) { pgs_small<R, 8>(n, A, x, b, lo, hi, fidx, iters); return; }
+    }
+    if constexpr (NR > 8) lcp_pgs<R>(n, A, x, b, lo, hi, fidx, iters);
+}
+
 // ------------------------------------------------------------------------ per-thread contact record
 template <typename R>
 struct ContactSink {      // where the LAST sub-step's contacts go (dartb_get_contacts); may be null
@@ -1362,7 +1414,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
             }
         }
         for (int r = 0; r < n; r++) A[r * n + r] *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
-        if (lcp_mode == 1) lcp_pgs<R>(n, A, x, bb, lo, hi, fidx, pgs_iters);
+        if (lcp_mode == 1) lcp_pgs_dispatch<R, NR>(n, A, x, bb, lo, hi, fidx, pgs_iters);
         else {
             uint8_t hrow[NR], srow[NR];
             for (int r = 0; r < n; r++) hrow[r] = (uint8_t)((hint >> (2 * rslot[r])) & 3u);

@@ -267,5 +267,5 @@ def test_batched_host_step_returns_fresh_arrays_of_reference_types():
     for i in range(80):
         env.step(rng.uniform(-1, 1, (128, 3)).astype(np.float32))
     assert np.array_equal(view, vc)
-    assert len(env._pool.slots) <= 4
+    assert len(env._pool.slots) <= 7     # the six arrays kept above + one in flight: the pool did not grow while stepping
     env.close()
