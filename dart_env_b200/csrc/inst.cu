@@ -1,6 +1,10 @@
 // inst.cu — one (topology, precision) instantiation of the kernels per translation unit.
 // Compiled by build.py with -DINST_TOPO=<TopoX|LOOP> -DINST_REAL=<float|double> -DINST_SUFFIX=<name>.
 #include <cstdlib>
+#include <cstdint>
+#ifndef DARTB_COOP_TMA_DEFAULT
+#define DARTB_COOP_TMA_DEFAULT 0
+#endif
 
 #include "kernels.cuh"
 
@@ -39,15 +43,30 @@ static int coop_warps() {   // warps per block (1, 2 or 4; DARTB_COOP_WARPS over
     return v;
 }
 #define COOP_WARPS coop_warps()
-static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a, const void* tab) {
-    const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a.n + per_block - 1) / per_block;
+static int coop_tma_mode() {   // DARTB_COOP_TMA: 0 plain loads, 1 TMA-staged state + lane table + obs store, 2 = actions too
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DARTB_COOP_TMA"); v = e ? atoi(e) : DARTB_COOP_TMA_DEFAULT; if (v < 0 || v > 2) v = 0; }
+    return v;
+}
+static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a_in, const void* tab) {
+    const int per_block = COOP_WARPS * Coop<T_>::WPW, grid = (a_in.n + per_block - 1) / per_block;
     const CoopLane<T_, R_>* t = (const CoopLane<T_, R_>*)tab;
+    StepArgs<R_> a = a_in;
+    // TMA staging needs full tiles whose pieces are 16-byte aligned multiples of 16 bytes
+    a.tma = 0;
+    if (coop_tma_mode() > 0 && a.n % per_block == 0 && (per_block * sizeof(R_)) % 16 == 0 && (per_block * K.n_obs * sizeof(float)) % 16 == 0 &&
+        ((uintptr_t)a.obs % 16) == 0 && ((size_t)a.n * sizeof(R_)) % 16 == 0) {
+        a.tma = 1;
+        if (coop_tma_mode() > 1 && (per_block * K.n_act * sizeof(float)) % 16 == 0 && ((uintptr_t)a.action % 16) == 0) a.tma = 2;
+    }
+    const size_t shm = a.tma ? coop_stage_offset<T_, R_>(COOP_WARPS, K.n_obs) + coop_stage_bytes<T_, R_>(COOP_WARPS, K.n_act)
+                             : coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs);
     // the fluid-force instantiation exists for capsule-free topologies only (the snake: the one task that has it);
     // dartb.cu::lower_into keeps fluid tasks on other topologies on the per-thread kernels
     if constexpr (T_::NS == 0) {
-        if (K.fluid_force) { k_env_step_coop<T_, R_, true><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t); return; }
+        if (K.fluid_force) { k_env_step_coop<T_, R_, true><<<grid, COOP_WARPS * 32, shm, st>>>(M, K, a, t); return; }
     }
-    k_env_step_coop<T_, R_, false><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, K.n_obs), st>>>(M, K, a, t);
+    k_env_step_coop<T_, R_, false><<<grid, COOP_WARPS * 32, shm, st>>>(M, K, a, t);
 }
 static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, const void* tab, int n, R_* q, R_* dq, const R_* tau, int lcp_mode,
                            int pgs_iters, const ContactSink<R_>& sink) {

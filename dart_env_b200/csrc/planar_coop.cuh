@@ -951,6 +951,38 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
     q += dt * dq;
 }
 
+// ------------------------------------------------------------------------ TMA 1-D bulk copies + mbarrier (sm_100a)
+// cp.async.bulk (SASS UBLKCP) moves a contiguous, 16-byte aligned run between global and shared memory without
+// touching the register file; completion of loads is counted in bytes on an mbarrier (SASS SYNCS), stores are tracked
+// by bulk groups.  Used by k_env_step_coop to stage a CTA's tile (lane table, q / dq rows, actions) with ONE elected
+// thread instead of ~20 LDGs per thread, and to write its observation tile with one bulk store.
+#ifndef DARTB_HOST_EMU
+DEVI uint32_t tma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVI void tma_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tma_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEVI void tma_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tma_smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVI void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tma_smem_u32(dst)), "l"(src), "r"(bytes), "r"(tma_smem_u32(bar)) : "memory");
+}
+DEVI void tma_mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(tma_smem_u32(bar)), "r"(phase) : "memory");
+}
+DEVI void tma_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the async proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tma_smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be reused / the CTA may exit
+}
+#endif
+
 // ======================================================================== kernels (G lanes per world)
 #ifdef DARTB_HOST_EMU
 #define COOP_GLOBAL
@@ -969,6 +1001,16 @@ DEVI void coop_substep(const PModel<R>& M, const CoopLane<T, R>& c, int gbase, R
 template <class T, typename R>
 __host__ __device__ constexpr size_t coop_shared_bytes(int warps, int n_obs) {
     return (size_t)warps * Coop<T>::WPW * sizeof(CoopRows<T, R>) + (size_t)warps * Coop<T>::WPW * n_obs * sizeof(float);
+}
+// + the TMA staging area of k_env_step_coop: [mbarrier | lane table | q rows | dq rows | actions], 16-byte aligned pieces
+template <class T, typename R>
+__host__ __device__ constexpr size_t coop_stage_bytes(int warps, int n_act) {
+    return 16 + sizeof(CoopLane<T, R>) * Coop<T>::G + 2 * (size_t)T::NB * warps * Coop<T>::WPW * sizeof(R) +
+           (((size_t)warps * Coop<T>::WPW * n_act * sizeof(float) + 15) / 16) * 16;
+}
+template <class T, typename R>
+__host__ __device__ constexpr size_t coop_stage_offset(int warps, int n_obs) {
+    return ((coop_shared_bytes<T, R>(warps, n_obs) + 15) / 16) * 16;
 }
 
 // exactly `skel.set_forces(tau); world.step()` (dart_env.py:174-175), no external forces
@@ -1009,9 +1051,46 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     float* sobs = reinterpret_cast<float*>(smraw + (size_t)nwarps * WPW * sizeof(CoopRows<T, R>)) + (size_t)warp * WPW * K.n_obs;
     // every global load of the step is issued up front and none depends on another (one DRAM round trip)
     const bool mine = wactive && l < NB;
-    const CoopLane<T, R> c = tab[l];
-    R q = mine ? a.q[(size_t)l * a.n + w] : (R)0, dq = mine ? a.dq[(size_t)l * a.n + w] : (R)0;
-    const R araw = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
+    CoopLane<T, R> c;
+    R q, dq, araw;
+#ifndef DARTB_HOST_EMU
+    if (a.tma) {
+        // TMA staging (a.tma is set by the launcher only for full, 16-byte aligned tiles): one elected thread issues
+        // 2*NB + 2 bulk copies for the whole CTA and everybody waits on one mbarrier
+        const int WPB = nwarps * WPW, wb0 = blockIdx.x * WPB;
+        unsigned char* st = smraw + coop_stage_offset<T, R>(nwarps, K.n_obs);
+        uint64_t* bar = reinterpret_cast<uint64_t*>(st);
+        CoopLane<T, R>* s_tab = reinterpret_cast<CoopLane<T, R>*>(st + 16);
+        R* s_q = reinterpret_cast<R*>(st + 16 + sizeof(CoopLane<T, R>) * G);
+        R* s_dq = s_q + NB * WPB;
+        float* s_act = reinterpret_cast<float*>(s_dq + NB * WPB);
+        if (threadIdx.x == 0) tma_mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t tab_b = sizeof(CoopLane<T, R>) * G, row_b = WPB * sizeof(R), act_b = WPB * K.n_act * sizeof(float);
+            tma_mbar_expect_tx(bar, tab_b + 2 * NB * row_b + (a.tma > 1 ? act_b : 0u));
+            tma_load_1d(s_tab, tab, tab_b, bar);
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                tma_load_1d(s_q + i * WPB, a.q + (size_t)i * a.n + wb0, row_b, bar);
+                tma_load_1d(s_dq + i * WPB, a.dq + (size_t)i * a.n + wb0, row_b, bar);
+            }
+            if (a.tma > 1) tma_load_1d(s_act, a.action + (size_t)wb0 * K.n_act, act_b, bar);
+        }
+        const int wl = warp * WPW + gi;    // world index inside the CTA
+        R araw_g = 0;
+        if (a.tma <= 1) araw_g = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
+        tma_mbar_wait(bar, 0);
+        c = s_tab[l];
+        q = mine ? s_q[l * WPB + wl] : (R)0; dq = mine ? s_dq[l * WPB + wl] : (R)0;
+        araw = a.tma > 1 ? ((wactive && l < K.n_act) ? (R)s_act[wl * K.n_act + l] : (R)0) : araw_g;
+    } else
+#endif
+    {
+        c = tab[l];
+        q = mine ? a.q[(size_t)l * a.n + w] : (R)0; dq = mine ? a.dq[(size_t)l * a.n + w] : (R)0;
+        araw = (wactive && l < K.n_act) ? (R)a.action[(size_t)w * K.n_act + l] : (R)0;
+    }
     const int el_in = (wactive && l == 0 && a.max_episode_steps > 0) ? a.elapsed[w] : 0;
     const uint32_t ep_in = (wactive && l == 0) ? a.episode[w] : 0u;
     uint32_t hint = wactive ? (uint32_t)a.hint[w] : 0xffffffffu;
@@ -1105,8 +1184,16 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
         if (height_obs) { if (l == 0) so[0] = (float)hgt; }
         else if (l == 1) so[0] = (float)q;
     }
-    __syncwarp();
+#ifndef DARTB_HOST_EMU
+    if (a.tma) {   // one bulk store of the CTA's [WPB, n_obs] observation tile (full tiles only, see the launcher)
+        __syncthreads();
+        const int WPB = nwarps * WPW;
+        if (threadIdx.x == 0)
+            tma_store_1d(a.obs + (size_t)blockIdx.x * WPB * K.n_obs, smraw + (size_t)nwarps * WPW * sizeof(CoopRows<T, R>), WPB * K.n_obs * sizeof(float));
+    } else
+#endif
     {
+        __syncwarp();
         const int cnt = a.n - wb < WPW ? a.n - wb : WPW;   // worlds of this warp that exist
         if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sobs[k];
     }

@@ -1030,10 +1030,11 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < NM; i++) {
-            R s = b[i];
+            // two interleaved partial sums: the row's dot product is the dependent chain of a Gauss-Seidel sweep
+            R s = b[i], s2 = 0;
 #pragma unroll
-            for (int j = 0; j < NM; j++) if (j != i) s -= A[i][j] * x[j];
-            s *= inv[i];
+            for (int j = 0; j < NM; j++) if (j != i) { if (j & 1) s2 -= A[i][j] * x[j]; else s -= A[i][j] * x[j]; }
+            s = (s + s2) * inv[i];
             R l = lo[i], h = hi[i];
             if (fi[i] >= 0) {
                 R xn = 0;
@@ -1055,6 +1056,9 @@ DEVI void lcp_pgs_dispatch(int n, const R* A, R* x, const R* b, const R* lo, con
     const int nmax = warp_max_active(n);
     if (nmax <= 4) { pgs_small<R, 4>(n, A, x, b, lo, hi, fidx, iters); return; }
     if constexpr (NR > 4) {
+        if (nmax <= 6) { pgs_small<R, 6>(n, A, x, b, lo, hi, fidx, iters); return; }
+    }
+    if constexpr (NR > 6) {
         if (nmax <= 8) { pgs_small<R, 8>(n, A, x, b, lo, hi, fidx, iters); return; }
     }
     if constexpr (NR > 8) lcp_pgs<R>(n, A, x, b, lo, hi, fidx, iters);
@@ -1089,6 +1093,8 @@ struct StepArgs {
     const uint8_t* mask; // reset mask (k_reset) or null
     int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
     int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for
+    int tma;             // k_env_step_coop: 1 = stage the CTA tile (lane table, q, dq) with TMA bulk copies and store the obs tile
+                         // with one, 2 = the actions too; 0 = plain loads / stores (set by the launcher, see inst.cu)
     uint64_t seed;
     int64_t world_offset;
     const uint64_t* seeds;   // [n] per-world seeds (VectorEnv.seed(list), sync_vector_env.py:50-57) or null

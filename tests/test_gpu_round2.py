@@ -269,3 +269,16 @@ def test_batched_host_step_returns_fresh_arrays_of_reference_types():
     assert np.array_equal(view, vc)
     assert len(env._pool.slots) <= 7     # the six arrays kept above + one in flight: the pool did not grow while stepping
     env.close()
+
+
+def test_tma_staged_prologue_is_bit_identical():
+    """k_env_step_coop with its CTA tile staged by TMA bulk copies (cp.async.bulk + mbarrier) and the observation tile
+    written by one bulk store (DARTB_COOP_TMA=1; 2 = the actions too) returns the same bits as the plain-load form."""
+    digests = {}
+    for mode in ("0", "1", "2"):
+        env = dict(os.environ, DARTB_COOP_TMA=mode)
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "coop_tma_check.py")], env=env, capture_output=True,
+                             text=True, timeout=600)
+        assert res.returncode == 0, res.stdout + res.stderr
+        digests[mode] = [ln for ln in res.stdout.splitlines() if ln.startswith("digest")][-1]
+    assert digests["0"] == digests["1"] == digests["2"], digests

@@ -30,6 +30,10 @@ def timeit(fn, K=300, do_flush=False):
 
 
 obs, rew, done = env._n_obs, env._n_rew, env._n_done
+keep = [None]
+def hold(i):
+    keep[0] = env.step(acts[i % 16])     # the caller keeps the last result: the pool alternates between two slots
+print("env.step(numpy), result held warm %.1f us   flushed %.1f us" % (timeit(hold), timeit(hold, do_flush=True)))
 print("env.step(numpy)            warm %.1f us   flushed %.1f us" % (timeit(lambda i: env.step(acts[i % 16])), timeit(lambda i: env.step(acts[i % 16]), do_flush=True)))
 print("engine.step_host           warm %.1f us   flushed %.1f us" % (timeit(lambda i: eng.step_host(acts[i % 16], obs, rew, done, True)), timeit(lambda i: eng.step_host(acts[i % 16], obs, rew, done, True), do_flush=True)))
 pg = np.empty_like(obs); pr = np.empty_like(rew); pd = np.empty_like(done)

@@ -79,6 +79,12 @@ elif mode == "r2big":   # round 2: the large-batch per-thread kernels, launch sh
             cfgs.append((env_id, n, b, "0", pgs, wpw))
     cfgs.append(("DartHopper-v1", 65536, "128", "0"))
     cfgs.append(("DartHopper-v1", 4096, "32", "0"))
+elif mode == "r2pgs":   # round 2: the PGS path (BASELINE configs 3 and 5) next to the exact solver
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096), ("DartHopper-v1", 65536)):
+        for pgs in ("", "30", "8", "1"):
+            cfgs.append((env_id, n, "128" if n > 4096 else "32", "0", pgs))
+    for pgs in ("", "30"):
+        cfgs.append(("DartSnake7Link-v1", 4096, "32", "2", pgs))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):

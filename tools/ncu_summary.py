@@ -104,7 +104,7 @@ if len(sr) > 2:
         if o in ("DFMA", "DMUL", "DADD"):
             f64 += (2 if o == "DFMA" else 1) * int(r[h2["Predicated-On Thread Instructions Executed"]])
     summary["fp64"] = {"flop_per_launch": f64, "note": "DADD+DMUL+2*DFMA thread instructions (fp64 mass-matrix core of the cooperative kernel)"}
-jpath = os.path.join(os.path.dirname(out), "r1_ncu_summary.json")
+jpath = os.path.join(os.path.dirname(out), os.path.basename(out).split("_")[0] + "_ncu_summary.json")   # r1_..., r2_...
 allj = json.load(open(jpath)) if os.path.exists(jpath) else {}
 allj[json_key] = summary
 json.dump(allj, open(jpath, "w"), indent=1)
@@ -113,7 +113,9 @@ with open(out + "_ncu_summary.md", "w") as fh:
     fh.write("| metric | " + " | ".join("launch %d" % k for k in range(len(launches))) + " | unit |\n|---|" + "---|" * (len(launches) + 1) + "\n")
     for k in keys:
         if k in hdr:
-            fh.write("| %s | %s | %s |\n" % (k, " | ".join(str(l.get(k)) for l in launches), units[hdr.index(k)]))
+            u = units[hdr.index(k)]
+            u = "byte" if u in ("Kbyte", "Mbyte", "Gbyte") else u     # tonum() already converted these to bytes
+            fh.write("| %s | %s | %s |\n" % (k, " | ".join(str(l.get(k)) for l in launches), u))
     fh.write("\nWarp stall sampling (all kernel instances, %% of samples): %s\n" % json.dumps(stalls))
     fh.write("\nInstructions / samples per source file: %s\n" % json.dumps(per_file))
     fh.write("\nDerived: %s\n" % json.dumps(summary, indent=1))
