@@ -160,6 +160,10 @@ template <> struct Num<double> {
 #ifndef DARTB_LCP_FORM
 #define DARTB_LCP_FORM 0
 #endif
+// K4 collision + contact rows of the per-thread kernels: 1 = one rolled loop over the capsules, 0 = unrolled per capsule
+#ifndef DARTB_ROLLED_COLLIDE
+#define DARTB_ROLLED_COLLIDE 1
+#endif
 
 // ------------------------------------------------------------------------ Philox4x32-10
 // identical to oracle/dart_oracle.c::orc_reset_uniform so reset noise is bit-identical
@@ -1024,17 +1028,26 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         R aii = 0;
 #pragma unroll
         for (int j = 0; j < NM; j++) { A[i][j] = (on && j < n) ? Ag[i * n + j] : (R)0; if (j == i) aii = A[i][j]; }
-        inv[i] = (on && !(aii < (R)1e-9)) ? (R)1 / aii : (R)0;     // 0: the row keeps x = 0 (lcp_pgs: aii < 1e-9)
+        const bool live = on && !(aii < (R)1e-9);
+        inv[i] = live ? (R)1 / aii : (R)0;
+        if (!live) { lo[i] = 0; hi[i] = 0; }     // padding / inert row (lcp_pgs: aii < 1e-9): the clamp keeps x = 0
     }
+    // A Gauss-Seidel sweep is ONE dependent chain through the rows.  Each row first sums everything that does not depend
+    // on the row just before it (those x are older: the scheduler overlaps that part with the previous rows), and only
+    // then adds the newest term: the chain per row is FMA -> FMUL -> min -> max instead of the whole dot product.
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < NM; i++) {
-            // two interleaved partial sums: the row's dot product is the dependent chain of a Gauss-Seidel sweep
-            R s = b[i], s2 = 0;
+            const int p = (i + NM - 1) % NM;      // the row updated just before row i
+            R s = b[i];
+            // oldest values first (rows after i: still the previous sweep's), then this sweep's in the order they appeared
 #pragma unroll
-            for (int j = 0; j < NM; j++) if (j != i) { if (j & 1) s2 -= A[i][j] * x[j]; else s -= A[i][j] * x[j]; }
-            s = (s + s2) * inv[i];
+            for (int j = i + 1; j < NM; j++) if (j != p) s -= A[i][j] * x[j];
+#pragma unroll
+            for (int j = 0; j < i; j++) if (j != p) s -= A[i][j] * x[j];
+            if (p != i) s -= A[i][p] * x[p];
+            s *= inv[i];
             R l = lo[i], h = hi[i];
             if (fi[i] >= 0) {
                 R xn = 0;
@@ -1044,7 +1057,7 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
             }
             s = s > h ? h : s;
             s = s < l ? l : s;
-            x[i] = inv[i] != 0 ? s : (R)0;
+            x[i] = s;
         }
     }
 #pragma unroll
@@ -1262,6 +1275,83 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
     R cpx[T::NSA], cpy[T::NSA], cnx[T::NSA], cny[T::NSA], cdep[T::NSA];
     int crow[T::NSA], cshape[T::NSA];
     const R INF = Num<R>::inf();
+#if DARTB_ROLLED_COLLIDE
+    // K4 as ONE rolled loop over the capsules (the unrolled form below carries NS copies of the closest-point walk
+    // and of the row assembly: 4.5 k of the 10.8 k distinct SASS instructions a HalfCheetah DART step executes, and
+    // the per-thread kernels are bound by instruction fetch: ncu r2, 71 % of the no_inst samples sit on 128-byte line
+    // starts).  The capsule frames come from the unrolled kinematics through small thread-local arrays; the Jacobian
+    // entries of non-ancestor bodies are masked with the capsule's ancestor set instead of being compiled out.
+    if constexpr (NS > 0) {
+        if (M.has_ground) {
+            const R inv_dt = (R)1 / dt;
+            R capx[NS], capy[NS], capdx[NS], capdy[NS];
+            static_for<0, NS>([&](auto sc) {
+                constexpr int s = decltype(sc)::value;
+                constexpr int b = T::sbody(s);
+                capx[s] = px[b] + cs[b] * M.scx[s] - sn[b] * M.scy[s]; capy[s] = py[b] + sn[b] * M.scx[s] + cs[b] * M.scy[s];
+                capdx[s] = cs[b] * M.sdx[s] - sn[b] * M.sdy[s]; capdy[s] = sn[b] * M.sdx[s] + cs[b] * M.sdy[s];
+            });
+#pragma unroll 1
+            for (int s = 0; s < NS; s++) {
+                const R ccx = capx[s], ccy = capy[s], adx = capdx[s], ady = capdy[s];
+                const R hl = M.shalf[s], rad = M.srad[s];
+                const R ex_ = hl * Num<R>::abs_(adx) + rad + (R)1e-5, ey_ = hl * Num<R>::abs_(ady) + rad + (R)1e-5;
+                const bool near_ = Num<R>::abs_(ccx - M.gcx) <= M.ghx + ex_ && Num<R>::abs_(ccy - M.gcy) <= M.ghy + ey_;
+                R lx = 0, ly = 0, ddx = 0, ddy = 0, d = INF;
+                if (near_) {
+                    closest_segment_box2<R>(ccx + hl * adx, ccy + hl * ady, ccx - hl * adx, ccy - hl * ady, M.gcx, M.gcy,
+                                            M.ghx, M.ghy, lx, ly, ddx, ddy);
+                    d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
+                }
+                if (!(d > rad)) {
+                    R nx, ny, depth, Px, Py;
+                    if (!(d < Num<R>::mindist())) {
+                        const R id = Num<R>::rcp_(d);
+                        nx = ddx * id; ny = ddy * id;
+                        depth = rad - d;
+                        const R k = (R)0.5 * (-rad - d);
+                        Px = lx + nx * k; Py = ly + ny * k;
+                    } else {
+                        nx = M.gupx; ny = M.gupy;
+                        depth = rad + (M.ghup - ((lx - M.gcx) * nx + (ly - M.gcy) * ny));
+                        Px = lx; Py = ly;
+                    }
+                    const R mu = M.smu[s];
+                    const bool fric = mu > (R)DK_FRICTION_THRESHOLD;
+                    const R tx = -ny, ty = nx;
+                    const int r0 = n;
+                    unsigned anc = 0;   // ancestors-or-self of this capsule's body
+                    static_for<0, NS>([&](auto sc) {
+                        constexpr int s2 = decltype(sc)::value;
+                        constexpr unsigned m2 = [] { unsigned m = 0; for (int j = 0; j < NB; j++) if (topo_is_ancestor<T>(j, T::sbody(s2))) m |= 1u << j; return m; }();
+                        if (s == s2) anc = m2;
+                    });
+                    R vn = 0, vt = 0;
+                    static_for<0, NB>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        R ax_, ay_;
+                        if constexpr (T::jtype(j) == PM_REV) { ax_ = -M.sgn[j] * (Py - py[j]); ay_ = M.sgn[j] * (Px - px[j]); }
+                        else { ax_ = uwx[j]; ay_ = uwy[j]; }
+                        const bool on = (anc >> j) & 1u;
+                        const R jn = on ? ax_ * nx + ay_ * ny : (R)0, jt = on ? ax_ * tx + ay_ * ty : (R)0;
+                        if (on) { vn += jn * dq[j]; vt += jt * dq[j]; }
+                        Jr[r0 * NB + j] = jn;
+                        if (fric) Jr[(r0 + 1) * NB + j] = jt;
+                    });
+                    R bounce = depth;
+                    if (bounce < 0) bounce = 0;
+                    else { bounce *= inv_dt * (R)DK_CONTACT_ERP; if (bounce > (R)DK_CONTACT_MAX_ERV) bounce = (R)DK_CONTACT_MAX_ERV; }
+                    bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1; rslot[r0] = 2 * s;
+                    n = r0 + 1;
+                    if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; rslot[r0 + 1] = 2 * s + 1; n = r0 + 2; }
+                    cpx[nc] = Px; cpy[nc] = Py; cnx[nc] = nx; cny[nc] = ny; cdep[nc] = depth; crow[nc] = r0 | (fric ? 0x100 : 0);
+                    cshape[nc] = s;
+                    nc++;
+                }
+            }
+        }
+    }
+#else
     if constexpr (NS > 0) {
         if (M.has_ground) {
             const R inv_dt = (R)1 / dt;
@@ -1326,6 +1416,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
             });
         }
     }
+#endif
     const int n_contact_rows = n;
     // joint-limit rows: q BEFORE this step's integration, dq AFTER the unconstrained update
     static_for<0, NB>([&](auto ic) {

@@ -191,6 +191,9 @@ class DartEnv:
         for x in (self._n_obs, self._n_rew, self._n_done, self._n_act):   # zero-copy without per-step driver queries
             capi.check(self.engine.L.dartb_register_host(self.engine.h, C.c_void_p(x.ctypes.data), x.nbytes))
         self._pool = None   # pinned output slots of the batched host path (built on first use)
+        # the host (numpy) path is synchronous: it keeps using the stream that was current when the engine was built
+        # instead of asking torch for the current stream on every step
+        self._host_stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
     @property
     def max_episode_steps(self):
@@ -330,7 +333,7 @@ class DartEnv:
                 slot = self._pool.take()
                 if slot is not None:
                     po, pr, pd, pt = slot["ptrs"]
-                    rc = eng.L.dartb_step_host_gym(eng.h, act_ptr, po, pr, pd, pt, int(self.auto_reset), eng._stream())
+                    rc = eng.L.dartb_step_host_gym(eng.h, act_ptr, po, pr, pd, pt, int(self.auto_reset), self._host_stream)
                     if rc:
                         capi.check(rc)
                     return slot["obs"], slot["rew"], slot["done"], ({"TimeLimit.truncated": slot["trunc"]} if pt is not None else {})
@@ -342,13 +345,13 @@ class DartEnv:
                 trunc = np.empty((n,), dtype=np.bool_) if self._max_episode_steps else None
                 rc = eng.L.dartb_step_host_gym(eng.h, act_ptr, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
                                                trunc.ctypes.data if trunc is not None else None, int(self.auto_reset),
-                                               eng._stream())
+                                               self._host_stream)
                 if rc:
                     capi.check(rc)
                 return obs, rew, done, ({"TimeLimit.truncated": trunc} if trunc is not None else {})
             # (the output arrays are this env's own page-locked buffers: their pointers are cached)
             rc = eng.L.dartb_step_host(eng.h, act_ptr, self._c_obs, self._c_rew, self._c_done, int(self.auto_reset),
-                                       eng._stream())
+                                       self._host_stream)
             if rc:
                 capi.check(rc)
             d = self._n_done  # bit 0 done, bit 1 truncated by the time limit (no extra transfer)

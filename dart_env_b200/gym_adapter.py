@@ -108,6 +108,12 @@ class DartVectorEnv(VectorEnv):
         self.env.close()
 
 
+# importable names for string entry points (`entry_point='dart_env_b200.gym_adapter:DartHopperEnv'`)
+for _id in IDS:
+    _cls = single_env_class(_id)
+    globals()[_cls.__name__] = _cls
+del _id, _cls
+
 _ORIG_VECTOR_MAKE = None
 
 

@@ -85,6 +85,10 @@ elif mode == "r2pgs":   # round 2: the PGS path (BASELINE configs 3 and 5) next 
             cfgs.append((env_id, n, "128" if n > 4096 else "32", "0", pgs))
     for pgs in ("", "30"):
         cfgs.append(("DartSnake7Link-v1", 4096, "32", "2", pgs))
+elif mode == "r2rc":   # round 2: per-thread kernels at their large-batch sizes, exact and PGS(30)
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
+        for pgs in ("", "30"):
+            cfgs.append((env_id, n, "128", "0", pgs))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):
