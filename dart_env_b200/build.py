@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 _SFX = os.environ.get("DARTB_SO_SUFFIX", "")
 OBJ = os.path.join(HERE, "build" + _SFX)
 SO = os.path.join(HERE, "libdartb%s.so" % _SFX)
-DEPS = ["dartb.cu", "inst.cu", "kernels.cuh", "planar_kernels.cuh", "planar_loop.cuh", "planar_coop.cuh", "task_kinds.cuh", "planar_model.h", "lower.h",
+DEPS = ["dartb.cu", "inst.cu", "kernels.cuh", "planar_kernels.cuh", "planar_loop.cuh", "planar_coop.cuh", "task_kinds.cuh", "warp_group.cuh", "planar_model.h", "lower.h",
         os.path.join("..", "..", "include", "dartb.h")]
 INSTANCES = [("hopper", "TopoHopper"), ("walker", "TopoWalker"), ("cheetah", "TopoCheetah"), ("snake", "TopoSnake"),
              ("loop", None)]

@@ -188,6 +188,155 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     }
 }
 
+// ------------------------------------------------------------------------ env.step() kernel, quad form
+// Four lanes per world (substep<..., G = 4>): lane / 4 picks the world inside the warp, all four lanes carry the same
+// state and the same task-layer arithmetic, lane % 4 == 0 writes.  Worlds per warp = 8.
+#ifndef DARTB_QUAD_MIN_BLOCKS
+#define DARTB_QUAD_MIN_BLOCKS 1
+#endif
+template <class T, typename R, bool FLUID>
+__global__ void __launch_bounds__(128, DARTB_QUAD_MIN_BLOCKS)
+k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
+    constexpr int NB = T::NB, G = 4, WPW = 32 / G;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / G, l = lane % G;
+    const int wb = (blockIdx.x * (blockDim.x >> 5) + warp) * WPW;   // first world of this warp
+    const int w = wb + gi;
+    const int cnt = min(WPW, a.n - wb);
+    const bool active = gi < cnt;
+    const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
+    float* sw = smem + warp * WPW * stage;
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
+    R q[NB], dq[NB], tau[NB], zero[NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        q[i] = active ? a.q[(size_t)i * a.n + w] : M.qinit[i];
+        dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
+        zero[i] = 0;
+    });
+    // per-world counters: every lane of the group reads them before lane 0 writes them back at the end
+    const int el_in = (active && a.max_episode_steps > 0) ? a.elapsed[w] : 0;
+    const uint32_t ep_in = active ? a.episode[w] : 0u;
+    uint64_t hint = active ? a.hint[w] : ~(uint64_t)0;
+    R a2 = 0;
+    if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[gi * K.n_act + j]; a2 += v * v; }
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        R t = 0;
+        if (active && K.dof_act[i] >= 0) {
+            R v = (R)sw[gi * K.n_act + K.dof_act[i]];
+            v = v > K.dof_hi[i] ? K.dof_hi[i] : v;
+            v = v < K.dof_lo[i] ? K.dof_lo[i] : v;
+            t = v * K.dof_scale[i];
+        }
+        tau[i] = t;
+    });
+    __syncwarp();
+    const R posbefore = q[0];
+    const ContactSink<R>* sink = (a.sink.count && l == 0) ? &a.sink : nullptr;
+#pragma unroll 1
+    for (int f = 0; f < K.frame_skip; f++) {
+        const ContactSink<R>* sk = (active && f == K.frame_skip - 1) ? sink : nullptr;
+        substep<T, R, false, FLUID, G>(M, q, dq, tau, zero, zero, zero, K.fluid_offset, K.fluid_coef, a.lcp_mode, a.pgs_iters, sk, w, hint);
+    }
+    const R ang = q[2];
+    R r = (q[0] - posbefore) * K.inv_dt_env * K.vel_weight;
+    r += K.alive_bonus;
+    r -= K.ctrl_cost * a2;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (K.limit_pen_dof == i) {
+            R pen = 0;
+            if ((M.qlo[i] - q[i]) > -K.limit_pen_margin) pen += (R)1.5;
+            if ((M.qhi[i] - q[i]) < K.limit_pen_margin) pen += (R)1.5;
+            r -= K.limit_pen_weight * pen;
+        }
+    });
+    r -= K.dev_cost * Num<R>::abs_(ang);
+    bool ok = true;
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (i >= 2 && !(Num<R>::abs_(q[i]) < K.state_bound)) ok = false;
+        if (i < 2 && !(Num<R>::abs_(q[i]) < Num<R>::inf())) ok = false;
+        if (!(Num<R>::abs_(dq[i]) < K.state_bound)) ok = false;
+    });
+    if (K.zero_reward_on_blowup && !ok) r = 0;
+    if (K.height_body >= 0) {
+        const R h = body_height<T, R>(M, K, q);
+        ok = ok && (h > K.height_lo) && (h < K.height_hi);
+    }
+    ok = ok && (Num<R>::abs_(ang) < K.ang_max);
+    bool done = !ok;
+    bool trunc = false;
+    int el_out = el_in;
+    if (active && a.max_episode_steps > 0) {
+        const int el = el_in + 1;
+        if (el >= a.max_episode_steps) { trunc = !done; done = true; }
+        el_out = (done && a.auto_reset) ? 0 : el;
+    }
+    const bool do_reset = active && done && a.auto_reset;
+    if (do_reset) {
+        reset_state<T, R>(M, K, reset_seed(a, w), reset_world(a, w), ep_in, q, dq);
+        hint = ~(uint64_t)0;
+    }
+    __syncwarp();
+    const bool writer = active && l == 0;
+    if (writer) {
+        if (a.max_episode_steps > 0) a.elapsed[w] = el_out;
+        if (do_reset) a.episode[w] = ep_in + 1;
+        a.hint[w] = hint;
+        write_obs<T, R>(M, K, q, dq, sw + gi * K.n_obs);
+    }
+    __syncwarp();
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (writer) {
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            a.q[(size_t)i * a.n + w] = q[i];
+            a.dq[(size_t)i * a.n + w] = dq[i];
+        });
+        if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
+        else {
+            a.reward[w] = (float)r;
+            a.done[w] = (uint8_t)((done ? 1 : 0) | (trunc ? 2 : 0));  // bit 0 done, bit 1 TimeLimit.truncated
+        }
+        if (a.truncated) a.truncated[w] = trunc ? 1 : 0;
+    }
+}
+
+// exactly `skel.set_forces(tau); world.step()`, quad form (no external forces)
+template <class T, typename R>
+__global__ void __launch_bounds__(128, DARTB_QUAD_MIN_BLOCKS)
+k_substep_quad(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, int lcp_mode, int pgs_iters,
+               const __grid_constant__ ContactSink<R> sink) {
+    constexpr int NB = T::NB, G = 4, WPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / G, l = lane % G;
+    const int w = (blockIdx.x * (blockDim.x >> 5) + warp) * WPW + gi;
+    const bool active = w < n;
+    const int wr = active ? w : 0;
+    R q[NB], dq[NB], tau[NB], zero[NB];
+    static_for<0, NB>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        q[i] = active ? qs[(size_t)i * n + wr] : M.qinit[i];
+        dq[i] = active ? dqs[(size_t)i * n + wr] : (R)0;
+        tau[i] = (active && tau_in) ? tau_in[(size_t)wr * NB + i] : (R)0;
+        zero[i] = 0;
+    });
+    uint64_t hint = ~(uint64_t)0;  // the literal World.step() drop-in is stateless
+    __syncwarp();                  // (every lane has read its world's state before lane 0 of a group writes it)
+    substep<T, R, false, false, G>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, lcp_mode, pgs_iters, (active && l == 0) ? &sink : nullptr, wr, hint);
+    __syncwarp();
+    if (active && l == 0)
+        static_for<0, NB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            qs[(size_t)i * n + w] = q[i];
+            dqs[(size_t)i * n + w] = dq[i];
+        });
+}
+
 // ------------------------------------------------------------------------ reset kernel
 template <class T, typename R>
 __global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
@@ -500,6 +649,10 @@ struct Launchers {
     void (*step_coop)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a, const void* lane_table);
     void (*substep_coop)(cudaStream_t st, const PModel<R>& M, const void* lane_table, int n, R* q, R* dq, const R* tau, int lcp_mode,
                          int pgs_iters, const ContactSink<R>& sink);
+    // quad form of the per-thread kernels (4 lanes per world); null for the loop variant.  They size their own grid.
+    void (*step_quad)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
+    void (*substep_quad)(cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, int lcp_mode, int pgs_iters,
+                         const ContactSink<R>& sink);
     void (*coop_table)(const PModel<R>& M, const PTask<R>& K, void* host_out);   // fills coop_table_bytes of per-lane constants
     size_t coop_table_bytes;
     int coop_lanes;   // lanes per world of the cooperative kernels (0: none)

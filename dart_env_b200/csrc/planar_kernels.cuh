@@ -1144,11 +1144,18 @@ DEVI void fk_positions(const PModel<R>& M, const R (&q)[T::NB], R (&cs)[T::NB], 
     });
 }
 
+#include "warp_group.cuh"   // group collectives + the row-per-lane LCP used by the quad form (G = 4) below
+
 // ------------------------------------------------------------------------ one DART time step
 // q, dq: in/out.  tau: generalized forces.  (eft, efx, efy): external spatial force per planar
 // body [torque about the body origin; fx; fy] in world axes (only read when FEXT).
 // FLUID: compute the snake fluid force (snake_7link.py:35-47) from the pre-step state instead.
-template <class T, typename R, bool FEXT, bool FLUID>
+// G = 1: one world per thread.  G = 4 (the QUAD form): the four lanes of a group hold the SAME world — K1-K4 and the row
+// assembly run redundantly and stay bit-identical across the group — and share the constraint phase: row r lives on lane
+// r % 4 (its impulse pass, its row of A = J M^-1 J^T, its row of the LCP tableau: GroupLcp<4>), dq += M^-1 J^T x is a
+// group sum.  A batch of 16384 worlds is then 2048 warps instead of 512 (3.5 per scheduler instead of < 1) and a warp
+// runs the union of 8 worlds' branches instead of 32.
+template <class T, typename R, bool FEXT, bool FLUID, int G = 1>
 DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&tau)[T::NB], const R (&eft)[T::NB],
                   const R (&efx)[T::NB], const R (&efy)[T::NB], R fluid_offset, R fluid_coef, int lcp_mode,
                   int pgs_iters, const ContactSink<R>* sink, int world, uint64_t& hint) {
@@ -1437,7 +1444,14 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
     });
 
     uint64_t new_hint = ~(uint64_t)0;
-    if (n > 0) {
+    // quad form: the shared constraint phase is entered by the WHOLE warp (its collectives need every lane) whenever any
+    // of its worlds has 1..8 rows; a world with more rows (a fallen walker) sits that phase out (nq = 0) and then takes the
+    // per-thread path on its four lanes, so a world's arithmetic never depends on which worlds share its warp
+    const int nq = (G > 1 && n <= 8) ? n : 0;
+    int nmaxq = 0;
+    bool quad = false;
+    if constexpr (G > 1) { nmaxq = coop_warp_max(nq); quad = nmaxq > 0; }
+    if (n > 0 || quad) {
         // plain (non-implicit) articulated inertia for the impulse passes
         R V0[NB], V1[NB], V2[NB], Ei[NB];
         {
@@ -1468,11 +1482,114 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 }
             });
         }
+        R A[NR * NR], x[NR];
+        if constexpr (G > 1) {
+          if (quad) {
+            const int l = (threadIdx.x & 31) % G, gbase = (threadIdx.x & 31) - l;
+            auto quad_tail = [&](auto ncc) {
+                constexpr int NCx = decltype(ncc)::value, RPL = NCx / G;
+                R MJq[RPL][NB], Aq[RPL][NCx], bq[RPL], loq[RPL], hiq[RPL], xq[RPL];
+                int fiq[RPL];
+                unsigned hinq[RPL], stq[RPL];
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    const int r = l + h * G;
+                    const bool valid = r < nq;
+                    const int rr = valid ? r : 0;
+                    // this lane's impulse pass (DART: applyUnitImpulse + getVelocityChange)
+                    R rh[NB], ur[NB], apt[NB], apx[NB], apy[NB], ddr[NB];
+                    static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; rh[i] = valid ? Jr[rr * NB + i] : (R)0; apt[i] = 0; apx[i] = 0; apy[i] = 0; });
+                    static_rfor<NB>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int par = T::parent(i);
+                        R pt = 0, pfx = 0, pfy = 0;
+                        if constexpr (topo_has_child<T>(i)) { pt = apt[i]; pfx = apx[i]; pfy = apy[i]; }
+                        R u;
+                        if constexpr (T::jtype(i) == PM_REV) u = rh[i] - M.sgn[i] * pt;
+                        else u = rh[i] - (uwx[i] * pfx + uwy[i] * pfy);
+                        ur[i] = u;
+                        if constexpr (par >= 0) {
+                            const R g = u * Ei[i];
+                            const R pa0 = pt + V0[i] * g, pa1 = pfx + V1[i] * g, pa2 = pfy + V2[i] * g;
+                            apt[par] += pa0 - ry[i] * pa1 + rx[i] * pa2; apx[par] += pa1; apy[par] += pa2;
+                        }
+                    });
+                    R a0[NB], a1[NB], a2[NB];
+                    static_for<0, NB>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int par = T::parent(i);
+                        R p0 = 0, p1 = 0, p2 = 0;
+                        if constexpr (par >= 0) { p0 = a0[par]; p1 = a1[par] - a0[par] * ry[i]; p2 = a2[par] + a0[par] * rx[i]; }
+                        const R dd = Ei[i] * (ur[i] - (V0[i] * p0 + V1[i] * p1 + V2[i] * p2));
+                        if constexpr (T::jtype(i) == PM_REV) { a0[i] = p0 + M.sgn[i] * dd; a1[i] = p1; a2[i] = p2; }
+                        else { a0[i] = p0; a1[i] = p1 + uwx[i] * dd; a2[i] = p2 + uwy[i] * dd; }
+                        ddr[i] = dd;
+                        MJq[h][i] = dd;
+                    });
+                    // its row of A = J M^-1 J^T (+ CFM on the diagonal): every J_s is known to every lane
+#pragma unroll
+                    for (int sidx = 0; sidx < NCx; sidx++) {
+                        R v = 0;
+                        if (sidx < nq) {
+                            static_for<0, NB>([&](auto jc) { constexpr int j = decltype(jc)::value; v += Jr[sidx * NB + j] * ddr[j]; });
+                            if (sidx == r) v *= (R)1 + (r < n_contact_rows ? (R)DK_CONTACT_CFM : (R)DK_LIMIT_CFM);
+                        }
+                        Aq[h][sidx] = valid ? v : (R)0;
+                    }
+                    bq[h] = valid ? bb[rr] : (R)0; loq[h] = valid ? lo[rr] : (R)0; hiq[h] = valid ? hi[rr] : (R)0;
+                    fiq[h] = valid ? fidx[rr] : -1;
+                    hinq[h] = valid ? (unsigned)((hint >> (2 * rslot[rr])) & 3u) : 3u;
+                    xq[h] = 0; stq[h] = 3u;
+                }
+                bool ok = lcp_mode != 1;
+                if (lcp_mode != 1) ok = GroupLcp<G, R, NCx>::solve(l, gbase, nq, nmaxq, Aq, bq, loq, hiq, fiq, hinq, xq, stq);
+                // PGS mode, or a group whose pivoting did not converge (never observed): gather A and run the per-thread
+                // solver on every lane of the group (identical inputs, identical results)
+                if (__any_sync(COOP_FULL, !ok)) {
+#pragma unroll
+                    for (int rr2 = 0; rr2 < NCx; rr2++)
+#pragma unroll
+                        for (int sidx = 0; sidx < NCx; sidx++) {
+                            const R v = gshfl<G>(Aq[rr2 / G][sidx], rr2 % G);
+                            if (rr2 < nq && sidx < nq) A[rr2 * nq + sidx] = v;
+                        }
+                    if (!ok) {
+                        if (lcp_mode == 1) lcp_pgs_dispatch<R, NR>(nq, A, x, bb, lo, hi, fidx, pgs_iters);
+                        else lcp_exact<R, NR>(nq, A, x, bb, lo, hi, fidx);
+#pragma unroll
+                        for (int h = 0; h < RPL; h++) { const int r = l + h * G; xq[h] = r < nq ? x[r] : (R)0; stq[h] = 3u; }
+                    }
+                }
+                // K7: dq += sum_r (M^-1 J_r^T) x_r, each lane's rows first, then over the group (same bits on every lane)
+                static_for<0, NB>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    R v = 0;
+#pragma unroll
+                    for (int h = 0; h < RPL; h++) if (l + h * G < nq) v += MJq[h][i] * xq[h];
+                    dq[i] += group_sum<G>(v);
+                });
+                // warm-start sets for the next step, and x of every row (contact read-back)
+                uint64_t clr = 0, setb = 0;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    const int r = l + h * G;
+                    if (r < nq) { clr |= (uint64_t)3 << (2 * rslot[r]); setb |= (uint64_t)(stq[h] & 3u) << (2 * rslot[r]); }
+                }
+                const unsigned clo = group_or<G>((unsigned)clr), chi = group_or<G>((unsigned)(clr >> 32));
+                const unsigned slo = group_or<G>((unsigned)setb), shi = group_or<G>((unsigned)(setb >> 32));
+                if (nq > 0) new_hint = (~(((uint64_t)chi << 32) | clo)) | (((uint64_t)shi << 32) | slo);
+#pragma unroll
+                for (int rr2 = 0; rr2 < NCx; rr2++) { const R v = gshfl<G>(xq[rr2 / G], rr2 % G); if (rr2 < nq) x[rr2] = v; }
+            };
+            if (nmaxq <= 4) quad_tail(std::integral_constant<int, 4>{});
+            else quad_tail(std::integral_constant<int, 8>{});
+          }
+        }
+        if (n > nq) {   // G == 1, or a quad world with more than 8 rows
         // M^-1 J^T, one impulse pass per row (DART: applyUnitImpulse + getVelocityChange), and row r of
         // A = J M^-1 J^T formed right away from the pass result still in registers (lower triangle,
         // mirrored: A is symmetric)
         R MJ[NR * NB];
-        R A[NR * NR], x[NR];
         for (int r = 0; r < n; r++) {
             R rh[NB], ur[NB], apt[NB], apx[NB], apy[NB], ddr[NB];
             static_for<0, NB>([&](auto ic) { constexpr int i = decltype(ic)::value; rh[i] = Jr[r * NB + i]; apt[i] = 0; apx[i] = 0; apy[i] = 0; });
@@ -1525,6 +1642,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
 #pragma unroll
             for (int j = 0; j < NB; j++) dq[j] += MJ[r * NB + j] * xr;
         }
+        }   // per-thread constraint phase
         if (sink && sink->data) {
             const R inv_dt = (R)1 / dt;
             for (int c = 0; c < nc && c < sink->maxc; c++) {

@@ -50,7 +50,7 @@ def _report(name, env_id, err):
 
 
 VARIANT = 0   # this module pins the one-world-per-thread kernels; tests/test_gpu_coop.py re-runs its tests with the
-              # lane-cooperative kernels (2).  (None = the engine's automatic choice by batch size.)
+              # lane-cooperative kernels (2), tests/test_gpu_quad.py with the quad form (3).  (None = automatic choice.)
 
 
 def _engine(models, env_id, n, **kw):
@@ -77,8 +77,8 @@ def _substep(models, env_id, g, f64):
     n = len(g["sub_q"])
     eng = _engine(models, env_id, n, f64=f64)
     eng.set_state(torch.tensor(g["sub_q"], dtype=dt, device=dev), torch.tensor(g["sub_dq"], dtype=dt, device=dev))
-    if VARIANT == 2:
-        # the cooperative kernel takes no external forces (the engine routes those to the per-thread kernel):
+    if VARIANT in (2, 3):
+        # the cooperative / quad kernels take no external forces (the engine routes those to the per-thread kernel):
         # step everything without them and let the caller look at the samples that have none
         eng.substep(torch.tensor(g["sub_tau"], dtype=dt, device=dev))
     else:
@@ -87,16 +87,16 @@ def _substep(models, env_id, g, f64):
     cnt, body, data = eng.contacts()
     torch.cuda.synchronize()
     out = q2.cpu().numpy(), dq2.cpu().numpy(), cnt.cpu().numpy(), body.cpu().numpy(), data.cpu().numpy()
-    assert eng.launch_count >= 3 and ("static:" in eng.kernel_name or "loop:" in eng.kernel_name or "coop:" in eng.kernel_name)
-    if VARIANT == 2:
-        assert "coop:" in eng.kernel_name
+    assert eng.launch_count >= 3 and any(k in eng.kernel_name for k in ("static:", "loop:", "coop:", "quad:"))
+    if VARIANT in (2, 3):
+        assert ("coop:" if VARIANT == 2 else "quad:") in eng.kernel_name
     eng.close()
     return out
 
 
 def _no_fext(g):
     """samples the cooperative kernel can be compared on (see _substep)"""
-    if VARIANT != 2:
+    if VARIANT not in (2, 3):
         return np.ones(len(g["sub_q"]), dtype=bool)
     return np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
 
@@ -107,7 +107,7 @@ def test_substep_fp64_matches_oracle_tightly(models, env_id):
     q2, dq2, cnt, body, data = _substep(models, env_id, g, True)
     nf = _no_fext(g)
     # (samples whose contact decision sits within 1e-9 of the threshold may flip: excluded from everything)
-    ok = nf & (g["sub_contact_margin"] > 1e-9) if VARIANT == 2 else nf
+    ok = nf & (g["sub_contact_margin"] > 1e-9) if VARIANT in (2, 3) else nf
     assert np.allclose(q2[ok], g["sub_q2"][ok], rtol=1e-9, atol=1e-10)
     assert np.allclose(dq2[ok], g["sub_dq2"][ok], rtol=1e-8, atol=1e-8)
     safe = nf & (g["sub_contact_margin"] > 1e-9)

@@ -219,10 +219,82 @@ def test_many_contact_states_large_column_classes(models):
                 S.append((s[0].copy(), s[1].copy(), tau.copy(), w.get_state()[1].copy()))
     assert len(S) >= 10
     q, dq, tau, ref = (np.array([s[k] for s in S]) for k in range(4))
-    for variant in (0, 2):
+    for variant in (0, 2, 3):
         _, dq2, *_r = emu.substep(m, task, q, dq, tau, None, f64=True, maxc=8, variant=variant)
         assert np.allclose(dq2, ref, rtol=1e-7, atol=1e-7), variant
         _, dq2, *_r = emu.substep(m, task, q, dq, tau, None, f64=False, maxc=8, variant=variant)
         ev = (np.abs(dq2 - ref) / (1 + np.abs(ref))).max(1)
         # (fp32: A is rank-deficient up to the CFM here, cond ~ 1e5; the cooperative kernel runs these classes in fp64)
         assert np.median(ev) < (2e-5 if variant == 2 else 1e-3) and ev.max() < 0.2, (variant, np.median(ev), ev.max())
+
+
+# ------------------------------------------------------------------ quad form of the per-thread kernels (substep<..., G = 4>)
+def _run_quad(models, env_id, f64, idx=None, **kw):
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
+    sel = np.where(nf)[0] if idx is None else np.asarray(idx)
+    out = emu.substep(models[env_id], SPECS[env_id].task, g["sub_q"][sel], g["sub_dq"][sel], g["sub_tau"][sel], None,
+                      f64=f64, maxc=8, variant=3, **kw)
+    return g, sel, out
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_quad_kernel_fp64_equals_oracle(models, env_id):
+    """four lanes per world: redundant K1-K4, constraint rows dealt out over the lanes, GroupLcp<4> == the 3-D fp64 oracle;
+    the emulation also checks that the lanes of a group hold the same bits (NaN marks otherwise)"""
+    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, True)
+    assert not np.isnan(q2).any()
+    safe = g["sub_contact_margin"][sel] > 1e-9
+    assert np.allclose(q2[safe], g["sub_q2"][sel][safe], rtol=1e-9, atol=1e-10)
+    assert np.allclose(dq2[safe], g["sub_dq2"][sel][safe], rtol=1e-8, atol=1e-8)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])
+    tie_ok = safe & (g["sub_tie_margin"][sel] > 1e-9)
+    assert np.array_equal(body[tie_ok], g["sub_contact_body"][sel][tie_ok])
+    assert np.allclose(data[tie_ok][..., :7], g["sub_contact_data"][sel][tie_ok][..., :7], atol=1e-6)
+    assert np.allclose(data[tie_ok][..., 7:], g["sub_contact_data"][sel][tie_ok][..., 7:], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("env_id", list(SPECS))
+def test_quad_kernel_fp32_within_tolerance(models, env_id):
+    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, False)
+    assert not np.isnan(q2).any()
+    safe = (g["sub_contact_margin"][sel] > 1e-4) & (g["sub_limit_margin"][sel] > 1e-4) & (g["sub_tie_margin"][sel] > 1e-4)
+    assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])
+    assert np.array_equal(body[safe], g["sub_contact_body"][sel][safe])
+    ev = (np.abs(dq2 - g["sub_dq2"][sel]) / (1 + np.abs(g["sub_dq2"][sel]))).max(1)
+    eq = (np.abs(q2 - g["sub_q2"][sel]) / (1 + np.abs(g["sub_q2"][sel]))).max(1)
+    deep = g["sub_contact_data"][sel][:, :, 6].max(1) > DEEP
+    assert ev[safe & ~deep].max() < TOL_SUB_DQ and eq[safe & ~deep].max() < TOL_SUB_Q
+    assert not (safe & deep).any() or (ev[safe & deep].max() < TOL_SUB_DQ_DEEP and eq[safe & deep].max() < TOL_SUB_Q_DEEP)
+
+
+def test_quad_kernel_pgs_equals_oracle_pgs(models):
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
+    idx = np.where(nf & (g["sub_ncontact"] > 0))[0][:30]
+    for iters in (1, 5, 30):
+        w = orc.OracleWorld(models[env_id])
+        w.set_option(1, 1); w.set_option(2, iters)
+        ref = []
+        for i in idx:
+            w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+            ref.append(np.concatenate(w.get_state()))
+        _, _, (q2, dq2, *_r) = _run_quad(models, env_id, True, idx=idx, lcp_mode=1, pgs_iters=iters)
+        assert np.allclose(np.concatenate([q2, dq2], 1), np.array(ref), rtol=1e-8, atol=1e-8)
+
+
+def test_quad_kernel_world_independent_of_warp_neighbours(models):
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
+    rows = g["sub_lcp_rows"]
+    small = np.where(nf & (rows >= 1) & (rows <= 4))[0][:8]
+    big = np.where(nf & (rows >= 9))[0][:8]      # oracle rows (3 per contact): sends the warp to the 8-column class or the per-thread path
+    assert len(small) == 8 and len(big) >= 2
+    for f64 in (True, False):
+        _, _, (qa, dqa, *_r) = _run_quad(models, env_id, f64, idx=small)
+        mixed = np.array([v for pair in zip(small, np.resize(big, 8)) for v in pair])
+        _, _, (qm, dqm, *_r) = _run_quad(models, env_id, f64, idx=mixed)
+        assert np.array_equal(qa, qm[0::2]) and np.array_equal(dqa, dqm[0::2])

@@ -89,6 +89,19 @@ elif mode == "r2rc":   # round 2: per-thread kernels at their large-batch sizes,
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
             cfgs.append((env_id, n, "128", "0", pgs))
+elif mode == "r2quad":   # round 2: quad form (3) vs one world per thread (0) vs lane-cooperative (2)
+    for env_id, sizes in (("DartWalker2d-v1", (16384, 8192, 4096)), ("DartHalfCheetah-v1", (16384, 8192, 4096)), ("DartHopper-v1", (65536, 16384, 4096)),
+                          ("DartSnake7Link-v1", (32768, 4096))):
+        for n in sizes:
+            for v in ("0", "3") + (("2",) if n <= 8192 else ()):
+                for pgs in ("", "30"):
+                    if pgs and v == "2":
+                        continue
+                    cfgs.append((env_id, n, "128", v, pgs))
+elif mode == "r2quadonly":   # register-cap builds of the quad form
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
+        for pgs in ("", "30"):
+            cfgs.append((env_id, n, "128", "3", pgs))
 elif mode == "lcp":
     for v in ("0", "1"):
         for pgs in ("", "1"):

@@ -94,6 +94,37 @@ static void run_substep_coop(const PModel<R>& M, int n, const double* q_in, cons
         for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)qs[(size_t)i * n + w]; dq_out[w * NB + i] = (double)dqs[(size_t)i * n + w]; }
 }
 
+// the quad form of the per-thread kernels (substep<..., G = 4>: four lanes per world) under the SIMT emulator;
+// mirrors csrc/kernels.cuh::k_substep_quad
+template <class T, typename R>
+static void run_substep_quad(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
+                             int lcp_mode, int pgs_iters, double* q_out, double* dq_out, int32_t* count, int32_t* body,
+                             float* data, int maxc) {
+    constexpr int NB = T::NB;
+    ContactSink<R> sink;
+    sink.count = count; sink.body = body; sink.data = data; sink.maxc = maxc;
+    const int grid = (n + 7) / 8;
+    simt::launch(grid, 0, [&] {
+        const int lane = threadIdx.x & 31, gi = lane / 4, l = lane % 4;
+        const int w = blockIdx.x * 8 + gi;
+        const bool active = w < n;
+        const int wr = active ? w : 0;
+        R q[NB], dq[NB], tau[NB], zero[NB];
+        for (int i = 0; i < NB; i++) {
+            q[i] = active ? (R)q_in[wr * NB + i] : M.qinit[i];
+            dq[i] = active ? (R)dq_in[wr * NB + i] : (R)0;
+            tau[i] = (active && tau_in) ? (R)tau_in[wr * NB + i] : (R)0;
+            zero[i] = 0;
+        }
+        uint64_t hint = ~(uint64_t)0;
+        substep<T, R, false, false, 4>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, lcp_mode, pgs_iters, (active && l == 0) ? &sink : nullptr, wr, hint);
+        // every lane of the group must hold the same bits: lane 1 checks against lane 0 through the outputs
+        if (active && l == 0) for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)q[i]; dq_out[w * NB + i] = (double)dq[i]; }
+        __syncwarp();
+        if (active && l == 3) for (int i = 0; i < NB; i++) if (q_out[w * NB + i] != (double)q[i] || dq_out[w * NB + i] != (double)dq[i]) { q_out[w * NB + i] = NAN; }
+    });
+}
+
 long g_emu_counters[8];
 long g_emu_hist[32];
 extern "C" void emu_hist(long* out, int reset) { for (int i = 0; i < 32; i++) { out[i] = g_emu_hist[i]; if (reset) g_emu_hist[i] = 0; } }
@@ -126,6 +157,14 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
         return 0;                                                                                                        \
     }
     RUNC(TopoHopper) RUNC(TopoWalker) RUNC(TopoCheetah) RUNC(TopoSnake)
+#define RUNQ(T)                                                                                                         \
+    if (variant == 3 && res.signature == T::sig) {                                                                       \
+        if (fext) { g_err = "the quad kernel takes no external forces"; return 1; }                                     \
+        if (f64) run_substep_quad<T, double>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
+        else run_substep_quad<T, float>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);          \
+        return 0;                                                                                                        \
+    }
+    RUNQ(TopoHopper) RUNQ(TopoWalker) RUNQ(TopoCheetah) RUNQ(TopoSnake)
 #define RUN(T)                                                                                                          \
     if (res.signature == T::sig) {                                                                                       \
         if (f64) run_substep<T, double>(res.m, n, q, dq, tau, fext, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, hints); \
