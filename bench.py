@@ -269,7 +269,8 @@ def roofline(r, kern_ms, peak, peak_src, prof, prof_src):
             "note": "fused per-world stepper: only the API-boundary I/O crosses HBM, so the HBM fraction is small by "
                     "construction; the kernel is bound by dependent-issue latency / instruction issue (issue_active_pct, "
                     "avg_active_lanes from the committed ncu capture of this kernel)"}
-    key = "%s/%d/%s" % (r.cfg["env"], r.n, "coop" if "coop:" in r.eng.kernel_name else "static")
+    form = "coop" if "coop:" in r.eng.kernel_name else ("quad" if "quad:" in r.eng.kernel_name else ("loop" if "loop:" in r.eng.kernel_name else "static"))
+    key = "%s/%d/%s" % (r.cfg["env"], r.n, form)
     p = prof.get(key) or prof.get(r.cfg["env"] if "coop:" in r.eng.kernel_name else r.cfg["env"] + "/static")
     if isinstance(p, dict):
         roof["traffic"] = p.get("dram_bytes_per_launch")

@@ -124,7 +124,7 @@ static int lower_into(dartb_engine* e) {
     const bool coop_ok = !(res.t.fluid_force && res.m.ns > 0);   // no cooperative fluid kernel for topologies with capsules
     if (topo < 0 || res.m.any_coulomb || want == 1 || res.t.kind != DARTB_TASK_LOCOMOTION) e->variant = 1;
     else if (want == 2 && coop_ok) e->variant = 2;
-    else if (want == 3) e->variant = 3;
+    else if (want == 3 || want == 4 || want == 5) e->variant = want;   // group forms: 4, 2, 8 lanes per world
     else if (!coop_ok) e->variant = 0;
     else if (want == 0) e->variant = 0;
     else {
@@ -146,7 +146,7 @@ static int lower_into(dartb_engine* e) {
     e->max_contacts = res.max_contacts;
     e->n_orig_bodies = e->model.n_bodies;
     const char* plane = std::fabs(res.m.en[2]) > 0.5 ? "planar-xy" : (std::fabs(res.m.en[1]) > 0.5 ? "planar-zx" : "planar-yz");
-    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string(e->variant == 2 ? "/coop:" : (e->variant == 3 ? "/quad:" : "/static:")) + topo_name(topo)) +
+    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string(e->variant == 2 ? "/coop:" : (e->variant == 3 ? "/quad:" : (e->variant == 4 ? "/pair:" : (e->variant == 5 ? "/octo:" : "/static:")))) + topo_name(topo)) +
                      (e->f64 ? "/f64" : "/f32");
     return 0;
 }
@@ -260,8 +260,8 @@ static int launch_step(dartb_engine* e, const float* action, float* obs, float* 
         CK(cudaGetLastError());
         return 0;
     }
-    if (e->variant == 3) {
-        LTab<R>::get(e).step_quad(st, Sel<R>::m(e), Sel<R>::t(e), a);
+    if (e->variant >= 3) {
+        LTab<R>::get(e).step_quad(st, e->variant == 4 ? 2 : (e->variant == 5 ? 8 : 4), Sel<R>::m(e), Sel<R>::t(e), a);
         e->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -300,8 +300,8 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
         if (coop_table_sync<R>(e, st)) return 1;
         LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->coop_tab, e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
     }
-    else if (e->variant == 3 && !fext)
-        LTab<R>::get(e).substep_quad(st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
+    else if (e->variant >= 3 && !fext)
+        LTab<R>::get(e).substep_quad(st, e->variant == 4 ? 2 : (e->variant == 5 ? 8 : 4), Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
     else
         LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
     e->launches++;
@@ -441,8 +441,8 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             for (int i = 0; i < e->model.n_bodies; i++) e->model.bodies[i].friction_coeff = value;
             return relower(e);
         case DARTB_OPT_KERNEL_VARIANT:
-            if (value != 0 && value != 1 && value != 2 && value != 3 && value != -1)
-                return fail("kernel variant must be -1 (auto), 0 (one world per thread), 1 (loop), 2 (lane-cooperative) or 3 (quad: 4 lanes per world)");
+            if (!(value == -1 || (value >= 0 && value <= 5 && value == (int)value)))
+                return fail("kernel variant must be -1 (auto), 0 (one world per thread), 1 (loop), 2 (lane-cooperative), 3 / 4 / 5 (group forms: 4 / 2 / 8 lanes per world)");
             e->variant_request = (int)value;
             return relower(e);
         case DARTB_OPT_WORLDS_PER_WARP:

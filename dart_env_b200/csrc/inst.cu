@@ -74,18 +74,26 @@ static void l_substep_coop(cudaStream_t st, const PModel<R_>& M, const void* tab
     k_substep_coop<T_, R_><<<grid, COOP_WARPS * 32, coop_shared_bytes<T_, R_>(COOP_WARPS, 0), st>>>(M, (const CoopLane<T_, R_>*)tab, n, q, dq, tau,
                                                                                                     lcp_mode, pgs_iters, sink);
 }
-// quad form: 4 warps per block, 8 worlds per warp
-static void l_step_quad(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
-    const int per_block = 4 * 8, grid = (a.n + per_block - 1) / per_block;
+// group ("quad") forms: 4 warps per block, 32 / lanes worlds per warp
+template <int G>
+static void launch_quad(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
+    const int per_block = 4 * (32 / G), grid = (a.n + per_block - 1) / per_block;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
-    const size_t shm = (size_t)4 * 8 * stage * sizeof(float);
-    if (K.fluid_force) k_env_step_quad<T_, R_, true><<<grid, 128, shm, st>>>(M, K, a);
-    else k_env_step_quad<T_, R_, false><<<grid, 128, shm, st>>>(M, K, a);
+    const size_t shm = (size_t)per_block * stage * sizeof(float);
+    if (K.fluid_force) k_env_step_quad<T_, R_, true, G><<<grid, 128, shm, st>>>(M, K, a);
+    else k_env_step_quad<T_, R_, false, G><<<grid, 128, shm, st>>>(M, K, a);
 }
-static void l_substep_quad(cudaStream_t st, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, int lcp_mode, int pgs_iters,
+static void l_step_quad(cudaStream_t st, int lanes, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
+    if (lanes == 2) launch_quad<2>(st, M, K, a);
+    else if (lanes == 8) launch_quad<8>(st, M, K, a);
+    else launch_quad<4>(st, M, K, a);
+}
+static void l_substep_quad(cudaStream_t st, int lanes, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, int lcp_mode, int pgs_iters,
                            const ContactSink<R_>& sink) {
-    const int per_block = 4 * 8, grid = (n + per_block - 1) / per_block;
-    k_substep_quad<T_, R_><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+    const int wpw = 32 / (lanes == 2 ? 2 : (lanes == 8 ? 8 : 4)), per_block = 4 * wpw, grid = (n + per_block - 1) / per_block;
+    if (lanes == 2) k_substep_quad<T_, R_, 2><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+    else if (lanes == 8) k_substep_quad<T_, R_, 8><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+    else k_substep_quad<T_, R_, 4><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
 }
 static void l_coop_table(const PModel<R_>& M, const PTask<R_>& K, void* out) { coop_build_table<T_, R_>(M, &K, (CoopLane<T_, R_>*)out); }
 #endif

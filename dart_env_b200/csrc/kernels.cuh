@@ -188,16 +188,16 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     }
 }
 
-// ------------------------------------------------------------------------ env.step() kernel, quad form
-// Four lanes per world (substep<..., G = 4>): lane / 4 picks the world inside the warp, all four lanes carry the same
-// state and the same task-layer arithmetic, lane % 4 == 0 writes.  Worlds per warp = 8.
+// ------------------------------------------------------------------------ env.step() kernel, group ("quad") form
+// G = 2, 4 or 8 lanes per world (substep<..., G>): lane / G picks the world inside the warp, all lanes of a group carry
+// the same state and the same task-layer arithmetic, lane % G == 0 writes.  Worlds per warp = 32 / G.
 #ifndef DARTB_QUAD_MIN_BLOCKS
 #define DARTB_QUAD_MIN_BLOCKS 1
 #endif
-template <class T, typename R, bool FLUID>
+template <class T, typename R, bool FLUID, int G>
 __global__ void __launch_bounds__(128, DARTB_QUAD_MIN_BLOCKS)
 k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
-    constexpr int NB = T::NB, G = 4, WPW = 32 / G;
+    constexpr int NB = T::NB, WPW = 32 / G;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = lane / G, l = lane % G;
@@ -307,11 +307,11 @@ k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
 }
 
 // exactly `skel.set_forces(tau); world.step()`, quad form (no external forces)
-template <class T, typename R>
+template <class T, typename R, int G>
 __global__ void __launch_bounds__(128, DARTB_QUAD_MIN_BLOCKS)
 k_substep_quad(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in /*[n,nd]*/, int lcp_mode, int pgs_iters,
                const __grid_constant__ ContactSink<R> sink) {
-    constexpr int NB = T::NB, G = 4, WPW = 32 / G;
+    constexpr int NB = T::NB, WPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = lane / G, l = lane % G;
     const int w = (blockIdx.x * (blockDim.x >> 5) + warp) * WPW + gi;
@@ -650,8 +650,8 @@ struct Launchers {
     void (*substep_coop)(cudaStream_t st, const PModel<R>& M, const void* lane_table, int n, R* q, R* dq, const R* tau, int lcp_mode,
                          int pgs_iters, const ContactSink<R>& sink);
     // quad form of the per-thread kernels (4 lanes per world); null for the loop variant.  They size their own grid.
-    void (*step_quad)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
-    void (*substep_quad)(cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, int lcp_mode, int pgs_iters,
+    void (*step_quad)(cudaStream_t st, int lanes, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);   // lanes per world: 2, 4, 8
+    void (*substep_quad)(cudaStream_t st, int lanes, const PModel<R>& M, int n, R* q, R* dq, const R* tau, int lcp_mode, int pgs_iters,
                          const ContactSink<R>& sink);
     void (*coop_table)(const PModel<R>& M, const PTask<R>& K, void* host_out);   // fills coop_table_bytes of per-lane constants
     size_t coop_table_bytes;

@@ -1487,7 +1487,7 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
           if (quad) {
             const int l = (threadIdx.x & 31) % G, gbase = (threadIdx.x & 31) - l;
             auto quad_tail = [&](auto ncc) {
-                constexpr int NCx = decltype(ncc)::value, RPL = NCx / G;
+                constexpr int NCx = decltype(ncc)::value, RPL = (NCx + G - 1) / G;
                 R MJq[RPL][NB], Aq[RPL][NCx], bq[RPL], loq[RPL], hiq[RPL], xq[RPL];
                 int fiq[RPL];
                 unsigned hinq[RPL], stq[RPL];

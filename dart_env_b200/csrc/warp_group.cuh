@@ -78,7 +78,8 @@ struct GroupLcp {
 #pragma unroll
         for (int cc = 0; cc < NC; cc++) {
             R mine = Tb[0][cc];
-            if constexpr (RPL > 1) if (kh == 1) mine = Tb[1][cc];
+#pragma unroll
+            for (int h2 = 1; h2 < RPL; h2++) if (kh == h2) mine = Tb[h2][cc];
             rk[cc] = gshfl<G>(mine, ko);
             if (cc == k) d = rk[cc];
         }
@@ -143,7 +144,8 @@ struct GroupLcp {
                     // x of the normal row this friction row hangs on
                     const int f = fricrow[h] ? fi[h] : l;
                     R xn = gshfl<G>(x[0], f % G);
-                    if constexpr (RPL > 1) { const R x1 = gshfl<G>(x[1], f % G); if (f / G == 1) xn = x1; }
+#pragma unroll
+                    for (int h2 = 1; h2 < RPL; h2++) { const R xh = gshfl<G>(x[h2], f % G); if (f / G == h2) xn = xh; }
                     R diag = 0;
 #pragma unroll
                     for (int cc = 0; cc < NC; cc++) { if (cc == l + h * G) diag = Tb[h][cc]; }

@@ -132,7 +132,7 @@ def test_batched_env_matches_reference_classes(env_id):
     # (actions cross the boundary as float32: tau carries their 6e-8 relative rounding)
     assert np.allclose(s[:, :nd], g["step_q2"], rtol=1e-6, atol=1e-7)
     assert np.allclose(ob, g["step_obs"], rtol=1e-6, atol=1e-6)   # observations cross the boundary as float32
-    assert np.allclose(rew, g["step_reward"], rtol=1e-8, atol=1e-8)
+    assert np.allclose(rew, g["step_reward"], rtol=1e-6, atol=1e-6)   # (the control cost sees the float32 action)
     assert np.array_equal(done, g["step_done"].astype(bool))
     env.close()
     # fp32 product path + gym surface for one env

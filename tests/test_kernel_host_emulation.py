@@ -229,20 +229,24 @@ def test_many_contact_states_large_column_classes(models):
 
 
 # ------------------------------------------------------------------ quad form of the per-thread kernels (substep<..., G = 4>)
-def _run_quad(models, env_id, f64, idx=None, **kw):
+QUAD_VARIANTS = {3: 4, 4: 2, 5: 8}   # kernel variant -> lanes per world
+
+
+def _run_quad(models, env_id, f64, idx=None, variant=3, **kw):
     g = np.load(os.path.join(GOLD, FILES[env_id]))
     nf = np.abs(g["sub_fext"]).reshape(len(g["sub_q"]), -1).max(1) == 0
     sel = np.where(nf)[0] if idx is None else np.asarray(idx)
     out = emu.substep(models[env_id], SPECS[env_id].task, g["sub_q"][sel], g["sub_dq"][sel], g["sub_tau"][sel], None,
-                      f64=f64, maxc=8, variant=3, **kw)
+                      f64=f64, maxc=8, variant=variant, **kw)
     return g, sel, out
 
 
+@pytest.mark.parametrize("variant", list(QUAD_VARIANTS))
 @pytest.mark.parametrize("env_id", list(SPECS))
-def test_quad_kernel_fp64_equals_oracle(models, env_id):
+def test_quad_kernel_fp64_equals_oracle(models, env_id, variant):
     """four lanes per world: redundant K1-K4, constraint rows dealt out over the lanes, GroupLcp<4> == the 3-D fp64 oracle;
     the emulation also checks that the lanes of a group hold the same bits (NaN marks otherwise)"""
-    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, True)
+    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, True, variant=variant)
     assert not np.isnan(q2).any()
     safe = g["sub_contact_margin"][sel] > 1e-9
     assert np.allclose(q2[safe], g["sub_q2"][sel][safe], rtol=1e-9, atol=1e-10)
@@ -254,9 +258,10 @@ def test_quad_kernel_fp64_equals_oracle(models, env_id):
     assert np.allclose(data[tie_ok][..., 7:], g["sub_contact_data"][sel][tie_ok][..., 7:], rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("variant", list(QUAD_VARIANTS))
 @pytest.mark.parametrize("env_id", list(SPECS))
-def test_quad_kernel_fp32_within_tolerance(models, env_id):
-    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, False)
+def test_quad_kernel_fp32_within_tolerance(models, env_id, variant):
+    g, sel, (q2, dq2, cnt, body, data) = _run_quad(models, env_id, False, variant=variant)
     assert not np.isnan(q2).any()
     safe = (g["sub_contact_margin"][sel] > 1e-4) & (g["sub_limit_margin"][sel] > 1e-4) & (g["sub_tie_margin"][sel] > 1e-4)
     assert np.array_equal(cnt[safe], g["sub_ncontact"][sel][safe])

@@ -98,6 +98,12 @@ elif mode == "r2quad":   # round 2: quad form (3) vs one world per thread (0) vs
                     if pgs and v == "2":
                         continue
                     cfgs.append((env_id, n, "128", v, pgs))
+elif mode == "r2group":   # round 2: group forms 2 / 4 / 8 lanes per world (variants 4 / 3 / 5) around the crossover sizes
+    for env_id, sizes in (("DartHopper-v1", (2048, 4096, 8192, 16384)), ("DartWalker2d-v1", (4096, 8192, 16384)), ("DartHalfCheetah-v1", (4096, 8192, 16384)),
+                          ("DartSnake7Link-v1", (2048, 4096, 8192))):
+        for n in sizes:
+            for v in ("4", "3", "5"):
+                cfgs.append((env_id, n, "128", v))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):

@@ -96,17 +96,18 @@ static void run_substep_coop(const PModel<R>& M, int n, const double* q_in, cons
 
 // the quad form of the per-thread kernels (substep<..., G = 4>: four lanes per world) under the SIMT emulator;
 // mirrors csrc/kernels.cuh::k_substep_quad
-template <class T, typename R>
+template <class T, typename R, int G>
 static void run_substep_quad(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
                              int lcp_mode, int pgs_iters, double* q_out, double* dq_out, int32_t* count, int32_t* body,
                              float* data, int maxc) {
     constexpr int NB = T::NB;
     ContactSink<R> sink;
     sink.count = count; sink.body = body; sink.data = data; sink.maxc = maxc;
-    const int grid = (n + 7) / 8;
+    constexpr int WPW = 32 / G;
+    const int grid = (n + WPW - 1) / WPW;
     simt::launch(grid, 0, [&] {
-        const int lane = threadIdx.x & 31, gi = lane / 4, l = lane % 4;
-        const int w = blockIdx.x * 8 + gi;
+        const int lane = threadIdx.x & 31, gi = lane / G, l = lane % G;
+        const int w = blockIdx.x * WPW + gi;
         const bool active = w < n;
         const int wr = active ? w : 0;
         R q[NB], dq[NB], tau[NB], zero[NB];
@@ -117,11 +118,11 @@ static void run_substep_quad(const PModel<R>& M, int n, const double* q_in, cons
             zero[i] = 0;
         }
         uint64_t hint = ~(uint64_t)0;
-        substep<T, R, false, false, 4>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, lcp_mode, pgs_iters, (active && l == 0) ? &sink : nullptr, wr, hint);
+        substep<T, R, false, false, G>(M, q, dq, tau, zero, zero, zero, (R)0, (R)0, lcp_mode, pgs_iters, (active && l == 0) ? &sink : nullptr, wr, hint);
         // every lane of the group must hold the same bits: lane 1 checks against lane 0 through the outputs
         if (active && l == 0) for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)q[i]; dq_out[w * NB + i] = (double)dq[i]; }
         __syncwarp();
-        if (active && l == 3) for (int i = 0; i < NB; i++) if (q_out[w * NB + i] != (double)q[i] || dq_out[w * NB + i] != (double)dq[i]) { q_out[w * NB + i] = NAN; }
+        if (active && l == G - 1) for (int i = 0; i < NB; i++) if (q_out[w * NB + i] != (double)q[i] || dq_out[w * NB + i] != (double)dq[i]) { q_out[w * NB + i] = NAN; }
     });
 }
 
@@ -158,10 +159,14 @@ extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task,
     }
     RUNC(TopoHopper) RUNC(TopoWalker) RUNC(TopoCheetah) RUNC(TopoSnake)
 #define RUNQ(T)                                                                                                         \
-    if (variant == 3 && res.signature == T::sig) {                                                                       \
-        if (fext) { g_err = "the quad kernel takes no external forces"; return 1; }                                     \
-        if (f64) run_substep_quad<T, double>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
-        else run_substep_quad<T, float>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc);          \
+    if (variant >= 3 && variant <= 5 && res.signature == T::sig) {                                                       \
+        if (fext) { g_err = "the group kernels take no external forces"; return 1; }                                    \
+        if (variant == 3) { if (f64) run_substep_quad<T, double, 4>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
+                            else run_substep_quad<T, float, 4>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); }        \
+        if (variant == 4) { if (f64) run_substep_quad<T, double, 2>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
+                            else run_substep_quad<T, float, 2>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); }        \
+        if (variant == 5) { if (f64) run_substep_quad<T, double, 8>(res.m, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); \
+                            else run_substep_quad<T, float, 8>(mf, n, q, dq, tau, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc); }        \
         return 0;                                                                                                        \
     }
     RUNQ(TopoHopper) RUNQ(TopoWalker) RUNQ(TopoCheetah) RUNQ(TopoSnake)
