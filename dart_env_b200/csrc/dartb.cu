@@ -50,11 +50,11 @@ __global__ void k_convert(size_t n, const S* src, D* dst) {
 // read once, through a C++11 function-local static (thread-safe initialisation): handles may be created from
 // several host threads
 struct EnvCfg {
-    int variant, block, wpw, zerocopy; long coop_max;
+    int variant, block, wpw, zerocopy; long coop_max, quad_max;
     EnvCfg() {
         auto geti = [](const char* k, long d) { const char* v = getenv(k); return v ? atol(v) : d; };
         variant = (int)geti("DARTB_VARIANT", -1); block = (int)geti("DARTB_BLOCK", 0); wpw = (int)geti("DARTB_WPW", 0);
-        zerocopy = (int)geti("DARTB_ZEROCOPY", 1); coop_max = geti("DARTB_COOP_MAX_WORLDS", -1);
+        zerocopy = (int)geti("DARTB_ZEROCOPY", 1); coop_max = geti("DARTB_COOP_MAX_WORLDS", -1); quad_max = geti("DARTB_QUAD_MAX_WORLDS", -1);
     }
 };
 static const EnvCfg& envcfg() { static const EnvCfg c; return c; }
@@ -121,21 +121,29 @@ static int lower_into(dartb_engine* e) {
     if (res.m.ns > LOOP_MAXS || res.m.nb > LOOP_MAXB) return fail("model too large for the planar kernels");
     const int forced_variant = envcfg().variant;
     const int want = e->variant_request >= 0 ? e->variant_request : forced_variant;
-    const bool coop_ok = !(res.t.fluid_force && res.m.ns > 0);   // no cooperative fluid kernel for topologies with capsules
-    if (topo < 0 || res.m.any_coulomb || want == 1 || res.t.kind != DARTB_TASK_LOCOMOTION) e->variant = 1;
+    // the compiled topologies carry the fluid force only where the reference has it (capsule-free: the snake); a fluid
+    // task on a skeleton with capsules runs on the topology-generic loop kernel
+    const bool coop_ok = true;
+    if (topo < 0 || res.m.any_coulomb || want == 1 || res.t.kind != DARTB_TASK_LOCOMOTION || (res.t.fluid_force && res.m.ns > 0)) e->variant = 1;
     else if (want == 2 && coop_ok) e->variant = 2;
-    else if (want == 3 || want == 4 || want == 5) e->variant = want;   // group forms: 4, 2, 8 lanes per world
+    else if (want == 3) e->variant = 3;
     else if (!coop_ok) e->variant = 0;
     else if (want == 0) e->variant = 0;
     else {
-        // auto: the cooperative kernel while the batch leaves warp schedulers idle at one world per thread
-        // (it trades ~2.5x more issued instructions per world for ~5x less latency per DART step)
-        // Crossovers measured on B200 (gpurun_out/sweep_coop*.log, us per env step, cooperative vs per-thread):
-        //   Hopper      4096: 38 vs 54    6144: 62 vs 54      Walker2d   4096: 107 vs 135   8192: 196 vs 156
-        //   HalfCheetah 8192: 340 vs 489  12288: 497 vs 492   Snake7Link 2048: 34 vs 39     4096: 59 vs 42
-        long lim = envcfg().coop_max;
-        if (lim < 0) lim = topo == TOPO_HOPPER ? 4736 : (topo == TOPO_WALKER ? 6144 : (topo == TOPO_CHEETAH ? 12288 : 2368));
-        e->variant = (e->n <= lim) ? 2 : 0;
+        // auto, by batch size.  Small batches: the lane-cooperative form (8 / 16 lanes per world: ~2.5x the instructions per
+        // world for ~5x less latency per DART step).  Mid-size batches: the quad form (4 lanes per world share the constraint
+        // phase: 4x the warps of the per-thread form, a warp runs the union of 8 worlds' branches instead of 32).  Large
+        // batches: one world per thread.  The quad form's PGS gathers A onto every lane, so PGS mode skips it.
+        // Crossovers measured on B200 (gpurun_out/r2g_sweep.log, r2h_sweep.log, r2i_xover.log; us per env step):
+        //   Hopper      2048: coop 32, quad 34     4096: quad 35.4, coop 38.8, static 47.7   8192: quad 41.9, static 55    16384: static 51.6, quad 75
+        //   Walker2d    4096: quad 85, coop 94, static 111     8192: quad 113, static 130, coop 178      16384: static 149, quad 213
+        //   HalfCheetah 4096: coop 168, quad 284, static 344   8192: coop 304, quad 372, static 420      16384: static 486, quad 509
+        //   Snake7Link  2048: quad 27.5, coop 34    4096: quad 31.4, static 41.6, coop 60     8192: quad 36.3     32768: static 55.7, quad 102
+        long lim_coop = envcfg().coop_max, lim_quad = envcfg().quad_max;
+        if (lim_coop < 0) lim_coop = topo == TOPO_HOPPER ? 2368 : (topo == TOPO_WALKER ? 2368 : (topo == TOPO_CHEETAH ? 11840 : 1184));
+        if (lim_quad < 0) lim_quad = topo == TOPO_HOPPER ? 11840 : (topo == TOPO_WALKER ? 11840 : (topo == TOPO_CHEETAH ? 0 : 14208));
+        if (e->lcp_mode == 1) lim_quad = 0;
+        e->variant = (e->n <= lim_coop) ? 2 : ((e->n <= lim_quad) ? 3 : 0);
     }
     e->topo = topo;
     e->coop_tab_dirty = true;
@@ -146,7 +154,7 @@ static int lower_into(dartb_engine* e) {
     e->max_contacts = res.max_contacts;
     e->n_orig_bodies = e->model.n_bodies;
     const char* plane = std::fabs(res.m.en[2]) > 0.5 ? "planar-xy" : (std::fabs(res.m.en[1]) > 0.5 ? "planar-zx" : "planar-yz");
-    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string(e->variant == 2 ? "/coop:" : (e->variant == 3 ? "/quad:" : (e->variant == 4 ? "/pair:" : (e->variant == 5 ? "/octo:" : "/static:")))) + topo_name(topo)) +
+    e->kernel_name = std::string(plane) + (e->variant == 1 ? std::string("/loop:generic") : std::string(e->variant == 2 ? "/coop:" : (e->variant == 3 ? "/quad:" : "/static:")) + topo_name(topo)) +
                      (e->f64 ? "/f64" : "/f32");
     return 0;
 }
@@ -260,8 +268,8 @@ static int launch_step(dartb_engine* e, const float* action, float* obs, float* 
         CK(cudaGetLastError());
         return 0;
     }
-    if (e->variant >= 3) {
-        LTab<R>::get(e).step_quad(st, e->variant == 4 ? 2 : (e->variant == 5 ? 8 : 4), Sel<R>::m(e), Sel<R>::t(e), a);
+    if (e->variant == 3) {
+        LTab<R>::get(e).step_quad(st, 4, Sel<R>::m(e), Sel<R>::t(e), a);
         e->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -300,8 +308,8 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
         if (coop_table_sync<R>(e, st)) return 1;
         LTab<R>::get(e).substep_coop(st, Sel<R>::m(e), e->coop_tab, e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
     }
-    else if (e->variant >= 3 && !fext)
-        LTab<R>::get(e).substep_quad(st, e->variant == 4 ? 2 : (e->variant == 5 ? 8 : 4), Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
+    else if (e->variant == 3 && !fext)
+        LTab<R>::get(e).substep_quad(st, 4, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
     else
         LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
     e->launches++;
@@ -433,7 +441,8 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
     switch (key) {
         case DARTB_OPT_LCP_MODE:
             if (value != 0 && value != 1) return fail("lcp mode must be 0 (exact) or 1 (PGS)");
-            e->lcp_mode = (int)value; return 0;
+            e->lcp_mode = (int)value;
+            return e->variant_request < 0 ? relower(e) : 0;   // the automatic kernel choice depends on the solver
         case DARTB_OPT_PGS_ITERS:
             if (value < 1 || value > 10000) return fail("bad PGS iteration count");
             e->pgs_iters = (int)value; return 0;
@@ -441,8 +450,8 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
             for (int i = 0; i < e->model.n_bodies; i++) e->model.bodies[i].friction_coeff = value;
             return relower(e);
         case DARTB_OPT_KERNEL_VARIANT:
-            if (!(value == -1 || (value >= 0 && value <= 5 && value == (int)value)))
-                return fail("kernel variant must be -1 (auto), 0 (one world per thread), 1 (loop), 2 (lane-cooperative), 3 / 4 / 5 (group forms: 4 / 2 / 8 lanes per world)");
+            if (!(value == -1 || (value >= 0 && value <= 3 && value == (int)value)))
+                return fail("kernel variant must be -1 (auto), 0 (one world per thread), 1 (loop), 2 (lane-cooperative) or 3 (quad: 4 lanes per world)");
             e->variant_request = (int)value;
             return relower(e);
         case DARTB_OPT_WORLDS_PER_WARP:

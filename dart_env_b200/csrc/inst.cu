@@ -26,8 +26,12 @@ static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, in
 #else
 typedef INST_TOPO T_;
 static void l_step(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
-    if (K.fluid_force) k_env_step<T_, R_, true><<<grid, bs, shm, st>>>(M, K, a);
-    else k_env_step<T_, R_, false><<<grid, bs, shm, st>>>(M, K, a);
+    // the fluid-force instantiation exists for capsule-free topologies only (the snake: the one task that has it);
+    // dartb.cu::lower_into sends fluid tasks on other topologies to the topology-generic loop kernel
+    if constexpr (T_::NS == 0) {
+        if (K.fluid_force) { k_env_step<T_, R_, true><<<grid, bs, shm, st>>>(M, K, a); return; }
+    }
+    k_env_step<T_, R_, false><<<grid, bs, shm, st>>>(M, K, a);
 }
 static void l_reset(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
     k_reset<T_, R_><<<grid, bs, shm, st>>>(M, K, a);
@@ -80,20 +84,20 @@ static void launch_quad(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K
     const int per_block = 4 * (32 / G), grid = (a.n + per_block - 1) / per_block;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     const size_t shm = (size_t)per_block * stage * sizeof(float);
-    if (K.fluid_force) k_env_step_quad<T_, R_, true, G><<<grid, 128, shm, st>>>(M, K, a);
-    else k_env_step_quad<T_, R_, false, G><<<grid, 128, shm, st>>>(M, K, a);
+    if constexpr (T_::NS == 0) {
+        if (K.fluid_force) { k_env_step_quad<T_, R_, true, G><<<grid, 128, shm, st>>>(M, K, a); return; }
+    }
+    k_env_step_quad<T_, R_, false, G><<<grid, 128, shm, st>>>(M, K, a);
 }
 static void l_step_quad(cudaStream_t st, int lanes, const PModel<R_>& M, const PTask<R_>& K, const StepArgs<R_>& a) {
-    if (lanes == 2) launch_quad<2>(st, M, K, a);
-    else if (lanes == 8) launch_quad<8>(st, M, K, a);
-    else launch_quad<4>(st, M, K, a);
+    (void)lanes;   // 2 and 8 lanes per world were measured and lost to 4 almost everywhere (profiles/r2_experiments.md section 6)
+    launch_quad<4>(st, M, K, a);
 }
 static void l_substep_quad(cudaStream_t st, int lanes, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, int lcp_mode, int pgs_iters,
                            const ContactSink<R_>& sink) {
-    const int wpw = 32 / (lanes == 2 ? 2 : (lanes == 8 ? 8 : 4)), per_block = 4 * wpw, grid = (n + per_block - 1) / per_block;
-    if (lanes == 2) k_substep_quad<T_, R_, 2><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
-    else if (lanes == 8) k_substep_quad<T_, R_, 8><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
-    else k_substep_quad<T_, R_, 4><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
+    (void)lanes;
+    const int per_block = 4 * 8, grid = (n + per_block - 1) / per_block;
+    k_substep_quad<T_, R_, 4><<<grid, 128, 0, st>>>(M, n, q, dq, tau, lcp_mode, pgs_iters, sink);
 }
 static void l_coop_table(const PModel<R_>& M, const PTask<R_>& K, void* out) { coop_build_table<T_, R_>(M, &K, (CoopLane<T_, R_>*)out); }
 #endif

@@ -119,7 +119,7 @@ enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
        DARTB_OPT_PGS_ITERS = 2,
        DARTB_OPT_FRICTION_ALL = 3,/* set_friction_coeff(mu) on every body (snake_7link.py:29-31) */
        DARTB_OPT_MAX_EPISODE_STEPS = 4,/* TimeLimit (gym/wrappers/time_limit.py:14-21); 0 = off */
-       DARTB_OPT_KERNEL_VARIANT = 5, /* -1 = auto, 0 = unrolled per-topology kernel (one world per thread), 1 = loop / topology-generic kernel, 2 = lane-cooperative kernel (8/16 lanes per world), 3 = quad form of the per-thread kernel (4 lanes per world share the constraint phase) */
+       DARTB_OPT_KERNEL_VARIANT = 5, /* -1 = auto, 0 = unrolled per-topology kernel (one world per thread), 1 = loop / topology-generic kernel, 2 = lane-cooperative kernel (8/16 lanes per world), 3 = quad form of the per-thread kernel (4 lanes per world share the constraint phase); auto: lane-cooperative, quad, per-thread by growing batch size */
        DARTB_OPT_WORLDS_PER_WARP = 6,/* launch shape of dartb_step: worlds per warp, 0 = auto; results do not depend on it */
        DARTB_OPT_CONTACTS = 7      /* 1 = dartb_step records world.collision_result.contacts of its last sub-step for
                                       dartb_get_contacts (walker2d.py:38-41); default 0: the record is 356 B per world

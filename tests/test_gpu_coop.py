@@ -59,19 +59,30 @@ def test_closed_loop_equals_per_thread_kernel_fp64(models, env_id):
 
 
 def test_automatic_kernel_choice_by_batch_size(models):
-    """Small batches run the cooperative form, large ones the per-thread form (dartb.cu::lower_into); either can
-    be forced.  Bit-exact shard == batch holds within one form; across forms trajectories agree to fp32 tolerance
-    and the reset noise (keyed by global world id) is identical."""
+    """Small batches run the cooperative form, mid-size ones the quad form, large ones the per-thread form
+    (dartb.cu::lower_into); each can be forced.  Bit-exact shard == batch holds within one form; across forms
+    trajectories agree to fp32 tolerance and the reset noise (keyed by global world id) is identical."""
     P.VARIANT = None
     try:
-        for env_id, small, large in (("DartHopper-v1", 4096, 16384), ("DartHalfCheetah-v1", 4096, 16384), ("DartSnake7Link-v1", 1024, 4096)):
-            a = P._engine(models, env_id, small, seed=1)
-            b = P._engine(models, env_id, large, seed=1)
-            assert "coop:" in a.kernel_name and "static:" in b.kernel_name, (a.kernel_name, b.kernel_name)
-            a.reset(); b.reset()
-            qa, _ = a.get_state(torch.float64)
-            qb, _ = b.get_state(torch.float64)
-            assert torch.equal(qa, qb[:small])      # same reset draws whichever kernel runs
-            a.close(); b.close()
+        for env_id, sizes in (("DartHopper-v1", ((2048, "coop:"), (4096, "quad:"), (16384, "static:"))),
+                              ("DartWalker2d-v1", ((2048, "coop:"), (8192, "quad:"), (16384, "static:"))),
+                              ("DartHalfCheetah-v1", ((4096, "coop:"), (16384, "static:"))),
+                              ("DartSnake7Link-v1", ((1024, "coop:"), (4096, "quad:"), (32768, "static:")))):
+            ref = None
+            for n, tag in sizes:
+                e = P._engine(models, env_id, n, seed=1)
+                assert tag in e.kernel_name, (env_id, n, e.kernel_name)
+                e.reset()
+                q, _ = e.get_state(torch.float64)
+                if ref is None:
+                    ref = q
+                else:
+                    assert torch.equal(ref, q[:ref.shape[0]])      # same reset draws whichever kernel runs
+                e.close()
+        # PGS mode skips the quad form (its PGS gathers A onto every lane)
+        e = P._engine(models, "DartWalker2d-v1", 8192, seed=1)
+        e.set_lcp(1, 30)
+        assert "static:" in e.kernel_name
+        e.close()
     finally:
         P.VARIANT = 2

@@ -79,39 +79,3 @@ def test_world_independent_of_warp_neighbours(models):
     qp, dqp = part.get_state(torch.float64)
     assert torch.equal(qf[24:40], qp) and torch.equal(dqf[24:40], dqp)
     full.close(); part.close()
-
-
-@pytest.mark.parametrize("variant,tag", [(4, "pair:"), (5, "octo:")])
-@pytest.mark.parametrize("env_id", ["DartHopper-v1", "DartHalfCheetah-v1"])
-def test_two_and_eight_lanes_per_world_equal_the_per_thread_kernel(models, env_id, variant, tag):
-    """the same group form with 2 and with 8 lanes per world: fp64 closed loop against the one-world-per-thread form, and the
-    fp32 single DART step inside the stated tolerance"""
-    spec = SPECS[env_id]
-    n, dev = 100, torch.device("cuda", 0)
-    gen = torch.Generator(device=dev); gen.manual_seed(7)
-    acts = [torch.rand((n, spec.task.n_act), generator=gen, device=dev) * 2 - 1 for _ in range(10)]
-    out = []
-    for v in (0, variant):
-        P.VARIANT = v
-        eng = P._engine(models, env_id, n, seed=6, f64=True)
-        obs = eng.reset()
-        rew = torch.empty((n,), dtype=torch.float32, device=dev); done = torch.empty((n,), dtype=torch.uint8, device=dev)
-        hist = []
-        for a in acts:
-            eng.step(a, obs, rew, done, True)
-            q, _ = eng.get_state(torch.float64)
-            hist.append((done.clone(), q.clone()))
-        assert (tag in eng.kernel_name) == (v == variant)
-        eng.close()
-        out.append(hist)
-    for t, ((d0, q0), (d1, q1)) in enumerate(zip(*out)):
-        same = (d0 == d1)
-        assert same.float().mean() > 0.99
-        if t < 4:
-            m = same.cpu().numpy()
-            assert np.allclose(q0.cpu().numpy()[m], q1.cpu().numpy()[m], rtol=1e-7, atol=1e-8)
-    P.VARIANT = variant
-    try:
-        P.test_substep_fp32_within_stated_tolerance(models, env_id)
-    finally:
-        P.VARIANT = 3

@@ -104,6 +104,12 @@ elif mode == "r2group":   # round 2: group forms 2 / 4 / 8 lanes per world (vari
         for n in sizes:
             for v in ("4", "3", "5"):
                 cfgs.append((env_id, n, "128", v))
+elif mode == "r2xover":   # round 2: the three forms around the automatic crossovers
+    for env_id, sizes in (("DartHopper-v1", (1024, 2048, 3072, 10240, 12288)), ("DartWalker2d-v1", (2048, 3072, 10240, 12288)),
+                          ("DartHalfCheetah-v1", (10240, 12288)), ("DartSnake7Link-v1", (1024, 12288, 16384))):
+        for n in sizes:
+            for v in (("2", "3") if n <= 3072 else (("0", "3") if env_id != "DartHalfCheetah-v1" else ("0", "2"))):
+                cfgs.append((env_id, n, "128", v))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
