@@ -140,8 +140,11 @@ static int lower_into(dartb_engine* e) {
         //   HalfCheetah 4096: coop 168, quad 284, static 344   8192: coop 304, quad 372, static 420      16384: static 486, quad 509
         //   Snake7Link  2048: quad 27.5, coop 34    4096: quad 31.4, static 41.6, coop 60     8192: quad 36.3     32768: static 55.7, quad 102
         long lim_coop = envcfg().coop_max, lim_quad = envcfg().quad_max;
-        if (lim_coop < 0) lim_coop = topo == TOPO_HOPPER ? 2368 : (topo == TOPO_WALKER ? 2368 : (topo == TOPO_CHEETAH ? 11840 : 1184));
-        if (lim_quad < 0) lim_quad = topo == TOPO_HOPPER ? 11840 : (topo == TOPO_WALKER ? 11840 : (topo == TOPO_CHEETAH ? 0 : 14208));
+        //   (crossovers, r2i_xover.log)  Hopper 2048: coop 32.5, quad 34.2; 3072: quad 34.5, coop 36.7; 10240: static 50.3, quad 65.1
+        //   Walker2d 2048: coop 54.5, quad 73.5; 3072: 80.1 / 79.6; 10240: static 130, quad 140   HalfCheetah 10240: coop 369, static 419;
+        //   12288: 438 / 441   Snake7Link 1024: quad 27.2, coop 28.9; 12288: static 45.2, quad 53.9
+        if (lim_coop < 0) lim_coop = topo == TOPO_HOPPER ? 2560 : (topo == TOPO_WALKER ? 2560 : (topo == TOPO_CHEETAH ? 12288 : 592));
+        if (lim_quad < 0) lim_quad = topo == TOPO_HOPPER ? 8880 : (topo == TOPO_WALKER ? 8880 : (topo == TOPO_CHEETAH ? 0 : 8880));
         if (e->lcp_mode == 1) lim_quad = 0;
         e->variant = (e->n <= lim_coop) ? 2 : ((e->n <= lim_quad) ? 3 : 0);
     }

@@ -110,6 +110,9 @@ elif mode == "r2xover":   # round 2: the three forms around the automatic crosso
         for n in sizes:
             for v in (("2", "3") if n <= 3072 else (("0", "3") if env_id != "DartHalfCheetah-v1" else ("0", "2"))):
                 cfgs.append((env_id, n, "128", v))
+elif mode == "r2q4mid":
+    for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 8192), ("DartWalker2d-v1", 4096), ("DartWalker2d-v1", 8192), ("DartSnake7Link-v1", 4096), ("DartHalfCheetah-v1", 8192)):
+        cfgs.append((env_id, n, "128", "3"))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
