@@ -206,17 +206,24 @@ class Runner:
         # actions: a pool of 64 pre-generated U(-1,1) batches cycled through (BASELINE.md regenerates them on the device
         # every step; a torch RNG kernel inside the timed region would not be this repo's kernel)
         self.pool = [(torch.rand((n, self.nact), generator=gen, device=self.dev) * 2 - 1).contiguous() for _ in range(64)]
-        self.gather = None
-        if cfg["allgather"] and world_size > 1:
+        self.gather, self.fused = None, None
+        if cfg.get("fused") and world_size > 1:
+            # the all-gather inside the step kernel: peer stores over NVLink into every rank's (symmetric-memory) buffer
+            from dart_env_b200.parallel import FusedObsGather
+            self.fused = FusedObsGather(self.env)
+        elif cfg["allgather"] and world_size > 1:
             self.gather = torch.empty((world_size * n, self.nobs), dtype=torch.float32, device=self.dev)
         self.env.reset()
         self.i = 0
 
     def one_step(self):
         env = self.env
-        self.eng.step(self.pool[self.i % 64], env._obs, env._rew, env._done, True)
-        if self.gather is not None:
-            self.dist.all_gather_into_tensor(self.gather, env._obs)
+        if self.fused is not None:
+            self.fused.step(self.pool[self.i % 64])
+        else:
+            self.eng.step(self.pool[self.i % 64], env._obs, env._rew, env._done, True)
+            if self.gather is not None:
+                self.dist.all_gather_into_tensor(self.gather, env._obs)
         self.i += 1
 
     def warm(self, W):
@@ -365,9 +372,15 @@ def run_ours(args, cfg, rank, local_rank, world_size):
             variants = [c]
             if cid == 3:
                 variants = [c, dict(c, lcp="exact")]
+            if cid == 4 and world_size > 1:
+                variants = [c, dict(c, fused=True)]
             out = {"env": c["env"], "worlds_per_gpu": c["worlds"], "runs": []}
             for v in variants:
-                x = Runner(torch, dist, v, rank, local_rank, world_size, args.seed)
+                try:
+                    x = Runner(torch, dist, v, rank, local_rank, world_size, args.seed)
+                except Exception as exc:   # (symmetric memory unavailable on this box: the fused gather is reported as such)
+                    out["runs"].append({"lcp": v["lcp"], "error": "%s: %s" % (type(exc).__name__, str(exc)[:200])})
+                    continue
                 x.warm(We)
                 barrier()
                 ms, nl = x.timed_flushed(Ke, flush)
@@ -378,9 +391,11 @@ def run_ours(args, cfg, rank, local_rank, world_size):
                        "value": x.n * world_size * Ke / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / Ke,
                        "value_l2_warm": x.n * world_size * Ke / (wm * 1e-3), "ms_per_step_l2_warm": wm / Ke, "steps": Ke,
                        "gpu_launches": int(nl), "done_fraction": x.done_fraction(),
-                       "parallelism": "worlds sharded x%d%s" % (world_size, ", all_gather_into_tensor(obs [%d,%d] fp32) inside every timed step"
-                                                                % (x.n * world_size, x.nobs) if x.gather is not None else
-                                                                (", obs all-gather is a no-op on one rank" if v["allgather"] else ", no collective"))}
+                       "parallelism": "worlds sharded x%d%s" % (world_size,
+                           ", obs all-gather FUSED into the step kernel (peer stores over NVLink into every rank's [%d,%d] buffer + one device-side barrier) inside every timed step"
+                           % (x.n * world_size, x.nobs) if x.fused is not None else
+                           (", NCCL all_gather_into_tensor(obs [%d,%d] fp32) inside every timed step" % (x.n * world_size, x.nobs) if x.gather is not None else
+                            (", obs all-gather is a no-op on one rank" if v["allgather"] else ", no collective")))}
                 if rank == 0:
                     run["roofline"] = roofline(x, ms / Ke, peak, peak_src, prof, prof_src)
                 out["runs"].append(run)

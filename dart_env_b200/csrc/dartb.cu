@@ -72,6 +72,8 @@ struct dartb_engine {
     dartb_model_t model; dartb_task_t task;   // kept so friction/options can re-lower
     void* q = nullptr; void* dq = nullptr;
     uint64_t* seeds = nullptr;                // [n] per-world seeds (dartb_seed_worlds) or null
+    float* obs_peer[DARTB_MAX_PEERS] = {};    // dartb_set_obs_peers: fused observation all-gather targets
+    int n_obs_peers = 0; long long obs_peer_off = 0;
     void* aux = nullptr;                      // [3][n] of Real: per-world task state (reacher target), or null
     void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
@@ -207,6 +209,8 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.aux = (R*)e->aux;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset; a.seeds = e->seeds;
+    a.n_obs_peers = e->n_obs_peers; a.obs_peer_off = e->obs_peer_off;
+    for (int p = 0; p < e->n_obs_peers; p++) a.obs_peer[p] = e->obs_peer[p];
     if (e->contacts) { a.sink.count = e->ccount; a.sink.body = e->cbody; a.sink.data = e->cdata; }
     a.sink.maxc = e->max_contacts;
     return a;
@@ -710,6 +714,15 @@ int dartb_substep_f64(dartb_handle_t e, const double* d_tau, const double* d_fex
     if (d_tau) { size_t k = (size_t)e->n * e->nd; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_tau, sc); tau = sc; e->launches++; }
     if (d_fext) { size_t k = (size_t)e->n * e->n_orig_bodies * 3; k_convert<double, float><<<(unsigned)((k + 255) / 256), 256, 0, st>>>(k, d_fext, sf); fx = sf; e->launches++; }
     return launch_substep<float>(e, tau, fx, st);
+}
+
+int dartb_set_obs_peers(dartb_handle_t e, void* const* d_peers, int32_t n_peers, int64_t float_offset) {
+    if (!e) return fail("null handle");
+    if (n_peers < 0 || n_peers > DARTB_MAX_PEERS) return fail("dartb_set_obs_peers: 0..8 peers");
+    if (n_peers > 0 && (!d_peers || float_offset < 0)) return fail("dartb_set_obs_peers: bad arguments");
+    for (int p = 0; p < n_peers; p++) { if (!d_peers[p]) return fail("dartb_set_obs_peers: null peer pointer"); e->obs_peer[p] = (float*)d_peers[p]; }
+    e->n_obs_peers = n_peers; e->obs_peer_off = float_offset;
+    return 0;
 }
 
 int dartb_set_aux(dartb_handle_t e, const double* d_aux, void* stream) {

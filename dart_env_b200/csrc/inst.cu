@@ -58,7 +58,7 @@ static void l_step_coop(cudaStream_t st, const PModel<R_>& M, const PTask<R_>& K
     StepArgs<R_> a = a_in;
     // TMA staging needs full tiles whose pieces are 16-byte aligned multiples of 16 bytes
     a.tma = 0;
-    if (coop_tma_mode() > 0 && a.n % per_block == 0 && (per_block * sizeof(R_)) % 16 == 0 && (per_block * K.n_obs * sizeof(float)) % 16 == 0 &&
+    if (coop_tma_mode() > 0 && a.n_obs_peers == 0 && a.n % per_block == 0 && (per_block * sizeof(R_)) % 16 == 0 && (per_block * K.n_obs * sizeof(float)) % 16 == 0 &&
         ((uintptr_t)a.obs % 16) == 0 && ((size_t)a.n * sizeof(R_)) % 16 == 0) {
         a.tma = 1;
         if (coop_tma_mode() > 1 && (per_block * K.n_act * sizeof(float)) % 16 == 0 && ((uintptr_t)a.action % 16) == 0) a.tma = 2;

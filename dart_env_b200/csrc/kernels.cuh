@@ -172,7 +172,7 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     // obs (of the reset state for auto-reset worlds: gym/vector/sync_vector_env.py:76-79)
     if (active) write_obs<T, R>(M, K, q, dq, sw + lane * K.n_obs);
     __syncwarp();
-    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) store_obs(a, (size_t)wb * K.n_obs + k, sw[k]);
     if (active) {
         static_for<0, NB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
@@ -290,7 +290,7 @@ k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
         write_obs<T, R>(M, K, q, dq, sw + gi * K.n_obs);
     }
     __syncwarp();
-    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) store_obs(a, (size_t)wb * K.n_obs + k, sw[k]);
     if (writer) {
         static_for<0, NB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
@@ -509,7 +509,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
         }
         if (active) write_obs_kind<R>(M, K, q, dq, tg, sw + lane * K.n_obs);
         __syncwarp();
-        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) store_obs(a, (size_t)wb * K.n_obs + k, sw[k]);
         if (active) {
             for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
             if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }
@@ -555,7 +555,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     }
     if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
     __syncwarp();
-    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sw[k];
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) store_obs(a, (size_t)wb * K.n_obs + k, sw[k]);
     if (active) {
         for (int i = 0; i < nb; i++) { a.q[(size_t)i * a.n + w] = q[i]; a.dq[(size_t)i * a.n + w] = dq[i]; }
         if (a.reward64) { a.reward64[w] = (double)r; a.done[w] = done ? 1 : 0; }

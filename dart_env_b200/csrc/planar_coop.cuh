@@ -944,7 +944,7 @@ COOP_GLOBAL void k_env_step_coop(const COOP_GRID_CONSTANT PModel<R> M, const COO
     {
         __syncwarp();
         const int cnt = a.n - wb < WPW ? a.n - wb : WPW;   // worlds of this warp that exist
-        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) a.obs[(size_t)wb * K.n_obs + k] = sobs[k];
+        if (cnt > 0) for (int k = lane; k < cnt * K.n_obs; k += 32) store_obs(a, (size_t)wb * K.n_obs + k, sobs[k]);
     }
     if (mine) { a.q[(size_t)l * a.n + w] = q; a.dq[(size_t)l * a.n + w] = dq; }
     if (wactive && l == 0) {

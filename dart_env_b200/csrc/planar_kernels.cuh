@@ -164,6 +164,10 @@ template <> struct Num<double> {
 #ifndef DARTB_ROLLED_COLLIDE
 #define DARTB_ROLLED_COLLIDE 1
 #endif
+// quad form: deal the narrow phase out over the four lanes (capsule s on lane s % 4) instead of repeating it on each
+#ifndef DARTB_QUAD_SPLIT_COLLIDE
+#define DARTB_QUAD_SPLIT_COLLIDE 1
+#endif
 
 // ------------------------------------------------------------------------ Philox4x32-10
 // identical to oracle/dart_oracle.c::orc_reset_uniform so reset noise is bit-identical
@@ -1111,8 +1115,18 @@ struct StepArgs {
     uint64_t seed;
     int64_t world_offset;
     const uint64_t* seeds;   // [n] per-world seeds (VectorEnv.seed(list), sync_vector_env.py:50-57) or null
+    // fused observation all-gather (dartb_set_obs_peers): every observation row is also stored into these buffers
+    // (peer GPUs' memory over NVLink, or local) at float offset obs_peer_off + its offset in `obs`
+    float* obs_peer[DARTB_MAX_PEERS];
+    int n_obs_peers;
+    long long obs_peer_off;
     ContactSink<R> sink;
 };
+template <typename R>
+DEVI void store_obs(const StepArgs<R>& a, size_t idx, float v) {
+    a.obs[idx] = v;
+    for (int p = 0; p < a.n_obs_peers; p++) a.obs_peer[p][a.obs_peer_off + (long long)idx] = v;
+}
 // Philox key of world w's reset draws: (seed, global world id), or (its own seed, 0) after a per-world seeding, so that
 // world i seeded s_i draws what a single env seeded s_i draws
 template <typename R>
@@ -1298,8 +1312,8 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                 capx[s] = px[b] + cs[b] * M.scx[s] - sn[b] * M.scy[s]; capy[s] = py[b] + sn[b] * M.scx[s] + cs[b] * M.scy[s];
                 capdx[s] = cs[b] * M.sdx[s] - sn[b] * M.sdy[s]; capdy[s] = sn[b] * M.sdx[s] + cs[b] * M.sdy[s];
             });
-#pragma unroll 1
-            for (int s = 0; s < NS; s++) {
+            // narrow phase of capsule s -> contact point / normal / depth (ODE dCollideCapsuleBox in the plane)
+            auto detect = [&](int s, R& Px, R& Py, R& nx, R& ny, R& depth) -> bool {
                 const R ccx = capx[s], ccy = capy[s], adx = capdx[s], ady = capdy[s];
                 const R hl = M.shalf[s], rad = M.srad[s];
                 const R ex_ = hl * Num<R>::abs_(adx) + rad + (R)1e-5, ey_ = hl * Num<R>::abs_(ady) + rad + (R)1e-5;
@@ -1310,50 +1324,83 @@ DEVI void substep(const PModel<R>& M, R (&q)[T::NB], R (&dq)[T::NB], const R (&t
                                             M.ghx, M.ghy, lx, ly, ddx, ddy);
                     d = Num<R>::sqrt_(ddx * ddx + ddy * ddy);
                 }
-                if (!(d > rad)) {
-                    R nx, ny, depth, Px, Py;
-                    if (!(d < Num<R>::mindist())) {
-                        const R id = Num<R>::rcp_(d);
-                        nx = ddx * id; ny = ddy * id;
-                        depth = rad - d;
-                        const R k = (R)0.5 * (-rad - d);
-                        Px = lx + nx * k; Py = ly + ny * k;
-                    } else {
-                        nx = M.gupx; ny = M.gupy;
-                        depth = rad + (M.ghup - ((lx - M.gcx) * nx + (ly - M.gcy) * ny));
-                        Px = lx; Py = ly;
-                    }
-                    const R mu = M.smu[s];
-                    const bool fric = mu > (R)DK_FRICTION_THRESHOLD;
-                    const R tx = -ny, ty = nx;
-                    const int r0 = n;
-                    unsigned anc = 0;   // ancestors-or-self of this capsule's body
-                    static_for<0, NS>([&](auto sc) {
-                        constexpr int s2 = decltype(sc)::value;
-                        constexpr unsigned m2 = [] { unsigned m = 0; for (int j = 0; j < NB; j++) if (topo_is_ancestor<T>(j, T::sbody(s2))) m |= 1u << j; return m; }();
-                        if (s == s2) anc = m2;
-                    });
-                    R vn = 0, vt = 0;
-                    static_for<0, NB>([&](auto jc) {
-                        constexpr int j = decltype(jc)::value;
-                        R ax_, ay_;
-                        if constexpr (T::jtype(j) == PM_REV) { ax_ = -M.sgn[j] * (Py - py[j]); ay_ = M.sgn[j] * (Px - px[j]); }
-                        else { ax_ = uwx[j]; ay_ = uwy[j]; }
-                        const bool on = (anc >> j) & 1u;
-                        const R jn = on ? ax_ * nx + ay_ * ny : (R)0, jt = on ? ax_ * tx + ay_ * ty : (R)0;
-                        if (on) { vn += jn * dq[j]; vt += jt * dq[j]; }
-                        Jr[r0 * NB + j] = jn;
-                        if (fric) Jr[(r0 + 1) * NB + j] = jt;
-                    });
-                    R bounce = depth;
-                    if (bounce < 0) bounce = 0;
-                    else { bounce *= inv_dt * (R)DK_CONTACT_ERP; if (bounce > (R)DK_CONTACT_MAX_ERV) bounce = (R)DK_CONTACT_MAX_ERV; }
-                    bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1; rslot[r0] = 2 * s;
-                    n = r0 + 1;
-                    if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; rslot[r0 + 1] = 2 * s + 1; n = r0 + 2; }
-                    cpx[nc] = Px; cpy[nc] = Py; cnx[nc] = nx; cny[nc] = ny; cdep[nc] = depth; crow[nc] = r0 | (fric ? 0x100 : 0);
-                    cshape[nc] = s;
-                    nc++;
+                if (d > rad) return false;
+                if (!(d < Num<R>::mindist())) {
+                    const R id = Num<R>::rcp_(d);
+                    nx = ddx * id; ny = ddy * id;
+                    depth = rad - d;
+                    const R k = (R)0.5 * (-rad - d);
+                    Px = lx + nx * k; Py = ly + ny * k;
+                } else {
+                    nx = M.gupx; ny = M.gupy;
+                    depth = rad + (M.ghup - ((lx - M.gcx) * nx + (ly - M.gcy) * ny));
+                    Px = lx; Py = ly;
+                }
+                return true;
+            };
+            // contact rows of capsule s: (normal, in-plane tangent)
+            auto assemble = [&](int s, R Px, R Py, R nx, R ny, R depth) {
+                const R mu = M.smu[s];
+                const bool fric = mu > (R)DK_FRICTION_THRESHOLD;
+                const R tx = -ny, ty = nx;
+                const int r0 = n;
+                unsigned anc = 0;   // ancestors-or-self of this capsule's body
+                static_for<0, NS>([&](auto sc) {
+                    constexpr int s2 = decltype(sc)::value;
+                    constexpr unsigned m2 = [] { unsigned m = 0; for (int j = 0; j < T::NB; j++) if (topo_is_ancestor<T>(j, T::sbody(s2))) m |= 1u << j; return m; }();
+                    if (s == s2) anc = m2;
+                });
+                R vn = 0, vt = 0;
+                static_for<0, NB>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    R ax_, ay_;
+                    if constexpr (T::jtype(j) == PM_REV) { ax_ = -M.sgn[j] * (Py - py[j]); ay_ = M.sgn[j] * (Px - px[j]); }
+                    else { ax_ = uwx[j]; ay_ = uwy[j]; }
+                    const bool on = (anc >> j) & 1u;
+                    const R jn = on ? ax_ * nx + ay_ * ny : (R)0, jt = on ? ax_ * tx + ay_ * ty : (R)0;
+                    if (on) { vn += jn * dq[j]; vt += jt * dq[j]; }
+                    Jr[r0 * NB + j] = jn;
+                    if (fric) Jr[(r0 + 1) * NB + j] = jt;
+                });
+                R bounce = depth;
+                if (bounce < 0) bounce = 0;
+                else { bounce *= inv_dt * (R)DK_CONTACT_ERP; if (bounce > (R)DK_CONTACT_MAX_ERV) bounce = (R)DK_CONTACT_MAX_ERV; }
+                bb[r0] = -vn + bounce; lo[r0] = 0; hi[r0] = INF; fidx[r0] = -1; rslot[r0] = 2 * s;
+                n = r0 + 1;
+                if (fric) { bb[r0 + 1] = -vt; lo[r0 + 1] = -mu; hi[r0 + 1] = mu; fidx[r0 + 1] = r0; rslot[r0 + 1] = 2 * s + 1; n = r0 + 2; }
+                cpx[nc] = Px; cpy[nc] = Py; cnx[nc] = nx; cny[nc] = ny; cdep[nc] = depth; crow[nc] = r0 | (fric ? 0x100 : 0);
+                cshape[nc] = s;
+                nc++;
+            };
+            if constexpr (G > 1 && DARTB_QUAD_SPLIT_COLLIDE && NS <= G) {   // (two capsules per lane measured slower: r2_experiments.md section 8)
+                // quad form: the narrow phase is dealt out over the lanes (capsule s on lane s % G), the contacts are
+                // then gathered in capsule order so that every lane assembles the same rows
+                constexpr int KS = (NS + G - 1) / G;
+                const int l = (threadIdx.x & 31) % G;
+                R rPx[KS], rPy[KS], rnx[KS], rny[KS], rdep[KS];
+                int rhas[KS];
+#pragma unroll
+                for (int k = 0; k < KS; k++) {
+                    const int s = l + k * G;
+                    rPx[k] = 0; rPy[k] = 0; rnx[k] = 0; rny[k] = 0; rdep[k] = 0; rhas[k] = 0;
+                    if (s < NS) rhas[k] = detect(s, rPx[k], rPy[k], rnx[k], rny[k], rdep[k]) ? 1 : 0;
+                }
+#pragma unroll 1
+                for (int s = 0; s < NS; s++) {
+                    const int o = s % G, k = s / G;
+                    R sPx = rPx[0], sPy = rPy[0], snx = rnx[0], sny = rny[0], sdep = rdep[0];
+                    int shas = rhas[0];
+#pragma unroll
+                    for (int k2 = 1; k2 < KS; k2++) if (k == k2) { sPx = rPx[k2]; sPy = rPy[k2]; snx = rnx[k2]; sny = rny[k2]; sdep = rdep[k2]; shas = rhas[k2]; }
+                    const int has = gshfl<G>(shas, o);
+                    const R Px = gshfl<G>(sPx, o), Py = gshfl<G>(sPy, o), nx = gshfl<G>(snx, o), ny = gshfl<G>(sny, o), depth = gshfl<G>(sdep, o);
+                    if (has) assemble(s, Px, Py, nx, ny, depth);
+                }
+            } else {
+#pragma unroll 1
+                for (int s = 0; s < NS; s++) {
+                    R Px, Py, nx, ny, depth;
+                    if (detect(s, Px, Py, nx, ny, depth)) assemble(s, Px, Py, nx, ny, depth);
                 }
             }
         }

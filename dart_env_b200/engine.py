@@ -102,6 +102,12 @@ class Engine:
         capi.check(fn(self.h, _ptr(q), _ptr(dq), self._stream()))
         return q, dq
 
+    def set_obs_peers(self, peer_ptrs, float_offset: int):
+        """Fused observation all-gather: step() also stores its observation rows into the buffers at `peer_ptrs`
+        (device pointers valid on this GPU, e.g. symmetric-memory buffer_ptrs) at `float_offset`.  [] switches it off."""
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        capi.check(self.L.dartb_set_obs_peers(self.h, arr, len(peer_ptrs), int(float_offset)))
+
     def set_aux(self, aux: torch.Tensor):
         """per-world task state [n, 3] float64 (the reacher's `self.target`, reacher2d.py:7,57-63)"""
         self._chk(aux, (self.n, 3), torch.float64)

@@ -43,6 +43,43 @@ def gather_batch(local: torch.Tensor, out: Optional[torch.Tensor] = None, group=
     return out
 
 
+class FusedObsGather:
+    """The observation all-gather INSIDE the step kernel: every rank's kernel stores its observation rows straight into
+    all ranks' gather buffers over NVLink (torch symmetric memory gives each rank the peers' buffer addresses), so the
+    transfer overlaps the stepping tile by tile and what remains after the kernel is one device-side barrier.
+
+        g = FusedObsGather(env)            # under torchrun, NCCL process group initialised
+        obs_all = g.step(actions)          # [world_size * n_local, n_obs], rows ordered by global world id
+
+    Raises RuntimeError where symmetric memory is unavailable (then use gather_batch: NCCL all_gather_into_tensor)."""
+
+    def __init__(self, env, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.env, self.eng = env, env.engine
+        group = group or dist.group.WORLD
+        self.ws, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n, no = self.eng.n, self.eng.n_obs
+        # two buffers, alternated per step: a rank may already be storing step k+1 into its peers while a peer's consumer of
+        # step k is still reading (it cannot reach step k+2 before every rank has passed the barrier of step k+1)
+        self.buf = symm.empty((2, self.ws * n, no), dtype=torch.float32, device=self.eng.device)
+        self.hdl = symm.rendezvous(self.buf, group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.k = 0
+
+    def step(self, actions: torch.Tensor):
+        env = self.env
+        n, no = self.eng.n, self.eng.n_obs
+        half = self.k & 1
+        self.eng.set_obs_peers(self.ptrs, half * self.ws * n * no + self.rank * n * no)
+        self.eng.step(actions, env._obs, env._rew, env._done, env.auto_reset)
+        self.hdl.barrier()                 # every rank's step kernel (and with it its peer stores) has completed
+        self.k += 1
+        return self.buf[half]
+
+    def close(self):
+        self.eng.set_obs_peers([], 0)
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Timing convention of bench.py: a multi-GPU step takes as long as its slowest rank."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

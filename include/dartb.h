@@ -28,6 +28,7 @@ extern "C" {
 
 #define DARTB_MAX_BODIES 24
 #define DARTB_MAX_SHAPES 24
+#define DARTB_MAX_PEERS  8
 #define DARTB_MAX_GROUND 4
 #define DARTB_MAX_ACT 16
 
@@ -195,6 +196,15 @@ int dartb_step_host_gym(dartb_handle_t h, const float* h_action, float* obs_out,
  * origins d_fext [n, n_bodies, 3] (bn.add_ext_force, snake_7link.py:47), may be NULL. */
 int dartb_substep(dartb_handle_t h, const float* d_tau, const float* d_fext, void* stream);
 int dartb_substep_f64(dartb_handle_t h, const double* d_tau, const double* d_fext, void* stream);
+
+/* Fused observation all-gather (the one optional collective, replacing the shared-memory observation buffer
+ * of gym/vector/async_vector_env.py:90-94).  After this call dartb_step ALSO stores every observation row it writes to
+ * d_obs into each of the n_peers buffers, at float offset `float_offset` + the row's offset in d_obs: with the peers'
+ * gather buffers mapped into this device's address space (NVLink peer access / symmetric memory) and float_offset =
+ * rank * n_worlds * n_obs, the all-gather happens inside the step kernel, tile by tile, instead of as a collective after
+ * it.  The caller synchronises the ranks before reading (any barrier: the stores are complete when the step kernel is).
+ * n_peers = 0 switches it off.  d_peers is a HOST array of device pointers. */
+int dartb_set_obs_peers(dartb_handle_t h, void* const* d_peers, int32_t n_peers, int64_t float_offset);
 
 /* Per-world auxiliary task state, [n, 3] fp64 (converted to the engine precision inside): the reacher's target
  * (`self.target`, reacher2d.py:7,57-63: world x, y, z).  Resets redraw it inside the kernel; these calls back the
