@@ -282,3 +282,33 @@ def test_tma_staged_prologue_is_bit_identical():
         assert res.returncode == 0, res.stdout + res.stderr
         digests[mode] = [ln for ln in res.stdout.splitlines() if ln.startswith("digest")][-1]
     assert digests["0"] == digests["1"] == digests["2"], digests
+
+
+@pytest.mark.parametrize("variant,n", [(0, 300), (2, 300), (3, 300)])
+def test_fused_obs_gather_peer_stores(variant, n):
+    """dartb_set_obs_peers: the step kernel also stores every observation row into the peer buffers at the rank's offset
+    (the obs all-gather fused into the kernel; on one GPU the "peers" are two more local buffers).  Every kernel form."""
+    from dart_env_b200.engine import Engine
+    from dart_env_b200.skel import load_model
+    spec = SPECS["DartWalker2d-v1"]
+    m = load_model(spec.skel, spec.dt)
+    m.enforce_limits()
+    eng = Engine(m, spec.task, n, seed=2, kernel_variant=variant)
+    eng.reset()
+    no = spec.task.n_obs
+    peers = [torch.full((3 * n, no), -7.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+    eng.set_obs_peers([p.data_ptr() for p in peers], 1 * n * no)        # "rank 1 of 3"
+    obs = torch.empty((n, no), dtype=torch.float32, device="cuda")
+    rew = torch.empty((n,), dtype=torch.float32, device="cuda"); done = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    for _ in range(5):
+        eng.step(torch.rand((n, 6), generator=gen, device="cuda") * 2 - 1, obs, rew, done, True)
+    torch.cuda.synchronize()
+    for p in peers:
+        assert torch.equal(p[n:2 * n], obs) and (p[:n] == -7.0).all() and (p[2 * n:] == -7.0).all()
+    eng.set_obs_peers([], 0)
+    peers[0].fill_(-7.0)
+    eng.step(torch.zeros((n, 6), device="cuda"), obs, rew, done, True)
+    torch.cuda.synchronize()
+    assert (peers[0] == -7.0).all()
+    eng.close()
