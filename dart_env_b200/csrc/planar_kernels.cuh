@@ -30,6 +30,7 @@
 
 #include <type_traits>
 
+#include "../../include/dartb.h"
 #include "planar_model.h"
 
 #ifndef DEVI
@@ -130,6 +131,8 @@ template <> struct Num<float> {
     static DEVI float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
     static DEVI float abs_(float x) { return fabsf(x); }
+    static DEVI float min_(float a, float b) { return fminf(a, b); }
+    static DEVI float max_(float a, float b) { return fmaxf(a, b); }
     static DEVI float inf() { return __int_as_float(0x7f800000); }
     static DEVI float inert() { return 1e-14f; }
     static DEVI float mindist() { return 1e-6f; }   // ODE dCollideCapsuleBox, dSINGLE build
@@ -141,6 +144,8 @@ template <> struct Num<double> {
     static DEVI double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static DEVI double rcp_(double x) { return 1.0 / x; }
     static DEVI double abs_(double x) { return fabs(x); }
+    static DEVI double min_(double a, double b) { return fmin(a, b); }
+    static DEVI double max_(double a, double b) { return fmax(a, b); }
     static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static DEVI double inert() { return 1e-14; }
     static DEVI double mindist() { return 1e-15; }  // ODE dCollideCapsuleBox, dDOUBLE build
@@ -1023,11 +1028,15 @@ DEVI void lcp_pgs(int n, const R* A, R* x, const R* b, const R* lo, const R* hi,
 template <typename R, int NM>
 DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R* hig, const int* fidxg, int iters) {
     R A[NM][NM], b[NM], lo[NM], hi[NM], x[NM], inv[NM];
-    int fi[NM];
+    bool isf[NM];
+    bool adjacent = true;
 #pragma unroll
     for (int i = 0; i < NM; i++) {
         const bool on = i < n;
-        b[i] = on ? bg[i] : (R)0; lo[i] = on ? log_[i] : (R)0; hi[i] = on ? hig[i] : (R)0; fi[i] = on ? fidxg[i] : -1;
+        const int fi = on ? fidxg[i] : -1;
+        isf[i] = fi >= 0;
+        if (fi >= 0 && fi != i - 1) adjacent = false;
+        b[i] = on ? bg[i] : (R)0; lo[i] = on ? log_[i] : (R)0; hi[i] = on ? hig[i] : (R)0;
         x[i] = 0;
         R aii = 0;
 #pragma unroll
@@ -1036,6 +1045,7 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         inv[i] = live ? (R)1 / aii : (R)0;
         if (!live) { lo[i] = 0; hi[i] = 0; }     // padding / inert row (lcp_pgs: aii < 1e-9): the clamp keeps x = 0
     }
+    if (!adjacent) { lcp_pgs<R>(n, Ag, xg, bg, log_, hig, fidxg, iters); return; }   // (not produced by this kernel's row layout)
     // A Gauss-Seidel sweep is ONE dependent chain through the rows.  Each row first sums everything that does not depend
     // on the row just before it (those x are older: the scheduler overlaps that part with the previous rows), and only
     // then adds the newest term: the chain per row is FMA -> FMUL -> min -> max instead of the whole dot product.
@@ -1052,16 +1062,11 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
             for (int j = 0; j < i; j++) if (j != p) s -= A[i][j] * x[j];
             if (p != i) s -= A[i][p] * x[p];
             s *= inv[i];
-            R l = lo[i], h = hi[i];
-            if (fi[i] >= 0) {
-                R xn = 0;
-#pragma unroll
-                for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
-                h = hi[i] * xn; l = -h;
-            }
-            s = s > h ? h : s;
-            s = s < l ? l : s;
-            x[i] = s;
+            // friction bounds +-mu x_n: a friction row directly follows its normal row (checked at load), so the sweep
+            // body has no data-dependent branch (a lone warp pays ~20 cycles per branch)
+            const R hf = hi[i] * (i > 0 ? x[i > 0 ? i - 1 : 0] : (R)0);
+            const R h = isf[i] ? hf : hi[i], l = isf[i] ? -hf : lo[i];
+            x[i] = Num<R>::max_(Num<R>::min_(s, h), l);     // (FMNMX; same result as the compare-and-select clamp for finite s)
         }
     }
 #pragma unroll
