@@ -131,6 +131,16 @@ template <> struct Num<float> {
     static DEVI float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
     static DEVI float abs_(float x) { return fabsf(x); }
+    // c ? a : b as ONE select instruction (the compiler turns nested ternaries into branch trees)
+#ifdef DARTB_HOST_EMU
+    static DEVI float sel_(bool c, float a, float b) { return c ? a : b; }
+#else
+    static DEVI float sel_(bool c, float a, float b) {
+        float r;
+        asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.f32 %0, %1, %2, p;\n}" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+        return r;
+    }
+#endif
     static DEVI float min_(float a, float b) { return fminf(a, b); }
     static DEVI float max_(float a, float b) { return fmaxf(a, b); }
     static DEVI float inf() { return __int_as_float(0x7f800000); }
@@ -144,6 +154,15 @@ template <> struct Num<double> {
     static DEVI double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static DEVI double rcp_(double x) { return 1.0 / x; }
     static DEVI double abs_(double x) { return fabs(x); }
+#ifdef DARTB_HOST_EMU
+    static DEVI double sel_(bool c, double a, double b) { return c ? a : b; }
+#else
+    static DEVI double sel_(bool c, double a, double b) {
+        double r;
+        asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+        return r;
+    }
+#endif
     static DEVI double min_(double a, double b) { return fmin(a, b); }
     static DEVI double max_(double a, double b) { return fmax(a, b); }
     static DEVI double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
@@ -406,13 +425,12 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
         // (`hin[i]`, the set the row ended in at the previous DART step, is used for the FRICTION rows
         // in stage 2 only: stick/slide persists between steps, while for the unilateral rows the
         // decoupled guess above measured better than the previous step's set under random actions)
-        const unsigned h = (hin && on) ? hin[i] : 3u;
-        unsigned s = 0;
-        if (!on || !(A[i][i] > Num<R>::inert())) s = 3;           // padding / inert row
-        else if (fi[i] >= 0) s = 3;                                 // friction rows wait for stage 2
-        else if (lo[i] == 0 && hi[i] == INF) s = b[i] > 0 ? 0u : 1u;
-        else if (hi[i] == 0 && lo[i] == -INF) s = b[i] < 0 ? 0u : 2u;
-        (void)h;
+        // (flat selects: padding / inert rows and friction rows -> 3; lower-unilateral -> free or at lo; upper-unilateral ->
+        //  free or at hi; any other box starts free)
+        const bool fixed = !on || !(A[i][i] > Num<R>::inert()) || fi[i] >= 0;
+        const bool lower = lo[i] == 0 && hi[i] == INF, upper = hi[i] == 0 && lo[i] == -INF;
+        const unsigned sl = b[i] > 0 ? 0u : 1u, su = b[i] < 0 ? 0u : 2u;
+        const unsigned s = fixed ? 3u : (lower ? sl : (upper ? su : 0u));
         st |= s << (2 * i);
     }
     bool ok = true;
@@ -428,17 +446,17 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
             bool any = false;
 #pragma unroll
             for (int i = 0; i < NM; i++) {
-                if (fi[i] >= 0 && i < n && A[i][i] > Num<R>::inert()) {
-                    R xn = 0;
+                // (flat selects again: one predicate per row instead of a branch tree)
+                const bool fr = fi[i] >= 0 && i < n && A[i][i] > Num<R>::inert();
+                R xn = 0;
 #pragma unroll
-                    for (int j = 0; j < NM; j++) if (j == fi[i]) xn = x[j];
-                    const R h = Num<R>::abs_(mu[i] * xn);
-                    hi[i] = h; lo[i] = -h;
-                    st &= ~(3u << (2 * i));
-                    const unsigned hh = hin ? hin[i] : 3u;
-                    if (h == 0) st |= 3u << (2 * i);
-                    else { any = true; if (hh < 3u) st |= hh << (2 * i); }   // hinted set, else free (sticking)
-                }
+                for (int j = 0; j < NM; j++) xn = Num<R>::sel_(j == fi[i], x[j], xn);
+                const R h = Num<R>::abs_(mu[i] * xn);
+                hi[i] = Num<R>::sel_(fr, h, hi[i]); lo[i] = Num<R>::sel_(fr, -h, lo[i]);
+                const unsigned hh = hin ? hin[i] : 3u;
+                const unsigned ns = h == 0 ? 3u : (hh < 3u ? hh : 0u);   // hinted set, else free (sticking)
+                st = fr ? ((st & ~(3u << (2 * i))) | (ns << (2 * i))) : st;
+                any = any || (fr && h != 0);
             }
             if (!any) break;
         }
@@ -451,9 +469,11 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
 #pragma unroll
             for (int i = 0; i < NM; i++) {
                 const unsigned si = (st >> (2 * i)) & 3u;
-                const R xb = si == 1 ? lo[i] : (si == 2 ? hi[i] : (R)0);
-                if (si != 0) x[i] = xb;
+                const R xb = Num<R>::sel_(si == 1, lo[i], Num<R>::sel_(si == 2, hi[i], (R)0));
+                x[i] = Num<R>::sel_(si != 0, xb, x[i]);
             }
+            // (this whole iteration body is written without data-dependent branches: selects and masked products only.
+            //  A lone warp per scheduler pays ~20 cycles for every branch; r2: 87 branches in 930 instructions before)
 #pragma unroll
             for (int i = 0; i < NM; i++) {
                 const bool fr = ((st >> (2 * i)) & 3u) == 0;
@@ -461,7 +481,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
 #pragma unroll
                 for (int j = 0; j < NM; j++) {
                     const bool fj = ((st >> (2 * j)) & 3u) == 0;
-                    if (!fj) r -= A[i][j] * x[j];
+                    r -= A[i][j] * (fj ? (R)0 : x[j]);
                 }
                 y[i] = fr ? r : (R)0;
             }
@@ -476,7 +496,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
                     R s = (fr && fj) ? A[i][j] : (i == j ? (R)1 : (R)0);
 #pragma unroll
                     for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-                    if (i == j) { if (!(s > 0)) { pd = false; s = 1; } L[i][i] = Num<R>::rsqrt_(s); }
+                    if (i == j) { const bool pos = s > 0; pd = pd && pos; L[i][i] = Num<R>::rsqrt_(pos ? s : (R)1); }
                     else L[i][j] = s * L[j][j];
                 }
             }
@@ -496,7 +516,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
                 y[i] = s * L[i][i];
             }
 #pragma unroll
-            for (int i = 0; i < NM; i++) if (((st >> (2 * i)) & 3u) == 0) x[i] = y[i];
+            for (int i = 0; i < NM; i++) x[i] = (((st >> (2 * i)) & 3u) == 0) ? y[i] : x[i];
             // infeasibilities (with rounding tolerances)
             unsigned bad = 0;  // bit i set: row i must change set
             int nbad = 0;
@@ -508,19 +528,19 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
 #pragma unroll
             for (int i = 0; i < NM; i++) {
                 const unsigned si = (st >> (2 * i)) & 3u;
-                if (si == 3) continue;
-                if (si == 0) {
-                    if (x[i] < lo[i] - tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (1u << (2 * i)); }
-                    else if (x[i] > hi[i] + tx) { bad |= 1u << i; nbad++; nst = (nst & ~(3u << (2 * i))) | (2u << (2 * i)); }
-                } else {
-                    R w = -b[i];
+                // a free row leaves its box / a bound row's w has the wrong sign (w is formed for every row: a few wasted
+                // products instead of a branch per row)
+                const bool below = x[i] < lo[i] - tx, above = x[i] > hi[i] + tx;
+                R w = -b[i];
 #pragma unroll
-                    for (int j = 0; j < NM; j++) w += A[i][j] * x[j];
-                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
-                    if ((si == 1 && w < -tw) || (si == 2 && w > tw)) {
-                        if (lo[i] < hi[i]) { bad |= 1u << i; nbad++; nst = nst & ~(3u << (2 * i)); }
-                    }
-                }
+                for (int j = 0; j < NM; j++) w += A[i][j] * x[j];
+                const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + sd[i] * S);
+                const bool wbad = ((si == 1 && w < -tw) || (si == 2 && w > tw)) && lo[i] < hi[i];
+                const bool badi = si == 0 ? (below || above) : wbad;     // (si == 3 makes wbad false)
+                const unsigned ns = si == 0 ? (below ? 1u : 2u) : 0u;     // the set the row moves to when it is infeasible
+                bad |= (badi ? 1u : 0u) << i;
+                nbad += badi ? 1 : 0;
+                nst = badi ? ((nst & ~(3u << (2 * i))) | (ns << (2 * i))) : nst;
             }
             EMU_COUNT(4, 1);
             if (nbad == 0) { done = true; break; }

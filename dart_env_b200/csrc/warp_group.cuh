@@ -182,8 +182,9 @@ struct GroupLcp {
                 R z[RPL], zg[NC], y[RPL];
 #pragma unroll
                 for (int h = 0; h < RPL; h++) {
-                    if (!done) cur[h] = st[h];
-                    z[h] = st[h] == 0 ? b[h] : (st[h] == 1 ? lo[h] : (st[h] == 2 ? hi[h] : (R)0));
+                    cur[h] = done ? cur[h] : st[h];
+                    // (selects, not branch trees: a warp with one or two resident neighbours pays for every branch)
+                    z[h] = Num<R>::sel_(st[h] == 0, b[h], Num<R>::sel_(st[h] == 1, lo[h], Num<R>::sel_(st[h] == 2, hi[h], (R)0)));
                 }
                 gather_rows(z, zg, nmax);
                 R axm = 0, Ssum = 0;
@@ -193,8 +194,8 @@ struct GroupLcp {
 #pragma unroll
                     for (int cc = 0; cc < NC; cc++) { s += Tb[h][cc] * zg[cc]; }
                     y[h] = s;
-                    const R xv = st[h] == 0 ? s : z[h];
-                    if (!done) x[h] = xv;
+                    const R xv = Num<R>::sel_(st[h] == 0, s, z[h]);
+                    x[h] = Num<R>::sel_(done, x[h], xv);
                     const R ax = valid[h] ? Num<R>::abs_(x[h]) : (R)0;
                     axm = ax > axm ? ax : axm;
                     Ssum += sd[h] * ax;
@@ -204,16 +205,13 @@ struct GroupLcp {
                 unsigned badm = 0, nst[RPL];
 #pragma unroll
                 for (int h = 0; h < RPL; h++) {
-                    nst[h] = st[h];
-                    bool bad = false;
-                    if (st[h] == 0) {
-                        if (x[h] < lo[h] - tx) { bad = true; nst[h] = 1; }
-                        else if (x[h] > hi[h] + tx) { bad = true; nst[h] = 2; }
-                    } else if (st[h] != 3) {
-                        const R w = y[h] - b[h];
-                        const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[h]) + sd[h] * S);
-                        if (((st[h] == 1 && w < -tw) || (st[h] == 2 && w > tw)) && lo[h] < hi[h]) { bad = true; nst[h] = 0; }
-                    }
+                    const bool below = x[h] < lo[h] - tx, above = x[h] > hi[h] + tx;
+                    const R w = y[h] - b[h];
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[h]) + sd[h] * S);
+                    const bool wbad = ((st[h] == 1 && w < -tw) || (st[h] == 2 && w > tw)) && lo[h] < hi[h];
+                    const bool bad = st[h] == 0 ? (below || above) : wbad;      // (st == 3 makes wbad false)
+                    const unsigned ns = st[h] == 0 ? (below ? 1u : 2u) : 0u;
+                    nst[h] = bad ? ns : st[h];
                     badm |= group_ballot<G>(bad && !done, gbase) << (h * G);
                 }
                 if (done) continue;

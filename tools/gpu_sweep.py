@@ -113,6 +113,15 @@ elif mode == "r2xover":   # round 2: the three forms around the automatic crosso
 elif mode == "r2q4mid":
     for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 8192), ("DartWalker2d-v1", 4096), ("DartWalker2d-v1", 8192), ("DartSnake7Link-v1", 4096), ("DartHalfCheetah-v1", 8192)):
         cfgs.append((env_id, n, "128", "3"))
+elif mode == "r2final":   # the automatic choice at every config size, exact and PGS(30)
+    for env_id, sizes in (("DartHopper-v1", (1024, 4096, 8192, 16384, 65536)), ("DartWalker2d-v1", (2048, 4096, 8192, 16384)),
+                          ("DartHalfCheetah-v1", (4096, 8192, 16384)), ("DartSnake7Link-v1", (1024, 4096, 8192, 32768))):
+        for n in sizes:
+            cfgs.append((env_id, n, "128", "-1"))
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096), ("DartHopper-v1", 4096)):
+        cfgs.append((env_id, n, "128", "-1", "30"))
+    for env_id, n, v in (("DartHopper-v1", 4096, "2"), ("DartHopper-v1", 4096, "0"), ("DartWalker2d-v1", 4096, "2"), ("DartHalfCheetah-v1", 8192, "3"), ("DartWalker2d-v1", 16384, "3")):
+        cfgs.append((env_id, n, "128", v))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
