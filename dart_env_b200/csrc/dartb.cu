@@ -75,6 +75,9 @@ struct dartb_engine {
     float* obs_peer[DARTB_MAX_PEERS] = {};    // dartb_set_obs_peers: fused observation all-gather targets
     int n_obs_peers = 0; long long obs_peer_off = 0;
     void* aux = nullptr;                      // [3][n] of Real: per-world task state (reacher target), or null
+    void* wpar = nullptr;                     // [4 nb + ns][n] of Real: per-world dynamics parameters (dartb_set_body_params), or null
+    std::vector<double> body_mass, body_mu;   // [n][n_bodies] as given to dartb_set_body_params (empty: the model's)
+    std::string signature;                    // topology signature of the lowered model
     void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
     uint64_t* hint = nullptr;                 // LCP warm-start sets, see planar_kernels.cuh::substep
@@ -126,7 +129,9 @@ static int lower_into(dartb_engine* e) {
     // the compiled topologies carry the fluid force only where the reference has it (capsule-free: the snake); a fluid
     // task on a skeleton with capsules runs on the topology-generic loop kernel
     const bool coop_ok = true;
-    if (topo < 0 || res.m.any_coulomb || want == 1 || res.t.kind != DARTB_TASK_LOCOMOTION || (res.t.fluid_force && res.m.ns > 0)) e->variant = 1;
+    // per-world dynamics parameters are read by the loop kernels only (the compiled topologies read one __grid_constant__ model)
+    const bool per_world = !e->body_mass.empty() || !e->body_mu.empty();
+    if (topo < 0 || res.m.any_coulomb || want == 1 || per_world || res.t.kind != DARTB_TASK_LOCOMOTION || (res.t.fluid_force && res.m.ns > 0)) e->variant = 1;
     else if (want == 2 && coop_ok) e->variant = 2;
     else if (want == 3) e->variant = 3;
     else if (!coop_ok) e->variant = 0;
@@ -151,6 +156,7 @@ static int lower_into(dartb_engine* e) {
         e->variant = (e->n <= lim_coop) ? 2 : ((e->n <= lim_quad) ? 3 : 0);
     }
     e->topo = topo;
+    e->signature = res.signature;
     e->coop_tab_dirty = true;
     e->md = res.m; e->td = res.t;
     lower::convert(res.m, e->mf);
@@ -207,6 +213,7 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.truncated = e->truncated;
     a.hint = e->hint;
     a.aux = (R*)e->aux;
+    a.wpar = (const R*)e->wpar;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset; a.seeds = e->seeds;
     a.n_obs_peers = e->n_obs_peers; a.obs_peer_off = e->obs_peer_off;
@@ -318,7 +325,7 @@ static int launch_substep(dartb_engine* e, const R* tau, const R* fext, cudaStre
     else if (e->variant == 3 && !fext)
         LTab<R>::get(e).substep_quad(st, 4, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, e->lcp_mode, e->pgs_iters, sink);
     else
-        LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink);
+        LTab<R>::get(e).substep(grid, bs, st, Sel<R>::m(e), e->n, (R*)e->q, (R*)e->dq, tau, fext, e->lcp_mode, e->pgs_iters, sink, (const R*)e->wpar);
     e->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -426,7 +433,7 @@ int dartb_create_f64(const dartb_model_t* model, const dartb_task_t* task, int32
 int dartb_destroy(dartb_handle_t e) {
     if (!e) return 0;
     DeviceGuard g(e->device);
-    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->aux); cudaFree(e->seeds); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
+    cudaFree(e->q); cudaFree(e->dq); cudaFree(e->aux); cudaFree(e->wpar); cudaFree(e->seeds); cudaFree(e->scratch); cudaFree(e->episode); cudaFree(e->elapsed);
     cudaFree(e->truncated); cudaFree(e->hint); cudaFree(e->ccount); cudaFree(e->cbody); cudaFree(e->cdata);
     if (e->coop_tab) cudaFree(e->coop_tab);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -436,11 +443,59 @@ int dartb_destroy(dartb_handle_t e) {
 }
 
 // options that change the lowered model: lower again and refresh the lane table (the only synchronising path)
+static int upload_body_params(dartb_engine* e);
 static int relower(dartb_engine* e) {
     if (lower_into(e)) return 1;
+    if (upload_body_params(e)) return 1;
     if (e->variant != 2) return 0;
     DeviceGuard g(e->device);
     return e->f64 ? coop_table_sync<double>(e, 0) : coop_table_sync<float>(e, 0);
+}
+
+// Per-world planar parameters from per-world DART bodynode masses / friction coefficients: every world's model is lowered
+// again with its own values (the weld merge mixes the masses of a group into its mass, COM and izz), so the kernel's numbers
+// are by construction what a single-world engine built from that model would use.
+static int upload_body_params(dartb_engine* e) {
+    const bool pm = !e->body_mass.empty(), pf = !e->body_mu.empty();
+    DeviceGuard g(e->device);
+    if (!pm && !pf) {
+        if (e->wpar) { cudaDeviceSynchronize(); cudaFree(e->wpar); e->wpar = nullptr; }
+        return 0;
+    }
+    std::vector<double> host;
+    std::string why = lower::body_param_table(e->model, e->task, e->n, pm ? e->body_mass.data() : nullptr, pf ? e->body_mu.data() : nullptr,
+                                              e->signature, e->md.nb, e->md.ns, host);
+    if (!why.empty()) return fail("dartb_set_body_params: " + why);
+    const size_t esz = e->f64 ? sizeof(double) : sizeof(float);
+    cudaDeviceSynchronize();   // a stepping call in flight may still read the old table
+    if (!e->wpar) CK(cudaMalloc(&e->wpar, host.size() * esz));
+    if (e->f64) CK(cudaMemcpy(e->wpar, host.data(), host.size() * esz, cudaMemcpyHostToDevice));
+    else {
+        std::vector<float> hf(host.begin(), host.end());
+        CK(cudaMemcpy(e->wpar, hf.data(), hf.size() * esz, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int dartb_set_body_params(dartb_handle_t e, const double* h_mass, const double* h_friction) {
+    if (!e) return fail("null handle");
+    const size_t k = (size_t)e->n * e->model.n_bodies;
+    for (size_t i = 0; i < k; i++) {
+        if (h_mass && !(h_mass[i] >= 0.0 && std::isfinite(h_mass[i]))) return fail("dartb_set_body_params: masses must be finite and >= 0");
+        if (h_friction && !(h_friction[i] >= 0.0 && std::isfinite(h_friction[i]))) return fail("dartb_set_body_params: friction coefficients must be finite and >= 0");
+    }
+    std::vector<double> old_m, old_f;
+    old_m.swap(e->body_mass); old_f.swap(e->body_mu);
+    if (h_mass) e->body_mass.assign(h_mass, h_mass + k);
+    if (h_friction) e->body_mu.assign(h_friction, h_friction + k);
+    if (relower(e)) {   // leave the engine as it was
+        e->body_mass.swap(old_m); e->body_mu.swap(old_f);
+        std::string keep = g_err;
+        relower(e);
+        g_err = keep;
+        return 1;
+    }
+    return 0;
 }
 
 int dartb_set_option(dartb_handle_t e, int32_t key, double value) {

@@ -20,8 +20,8 @@ static void l_reset(int grid, int bs, size_t shm, cudaStream_t st, const PModel<
     k_reset_loop<R_><<<grid, bs, shm, st>>>(M, K, a);
 }
 static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, const R_* fext,
-                      int lcp_mode, int pgs_iters, const ContactSink<R_>& sink) {
-    k_substep_loop<R_><<<grid, bs, 0, st>>>(M, n, q, dq, tau, fext, lcp_mode, pgs_iters, sink);
+                      int lcp_mode, int pgs_iters, const ContactSink<R_>& sink, const R_* wpar) {
+    k_substep_loop<R_><<<grid, bs, 0, st>>>(M, n, q, dq, tau, fext, lcp_mode, pgs_iters, sink, wpar);
 }
 #else
 typedef INST_TOPO T_;
@@ -37,7 +37,7 @@ static void l_reset(int grid, int bs, size_t shm, cudaStream_t st, const PModel<
     k_reset<T_, R_><<<grid, bs, shm, st>>>(M, K, a);
 }
 static void l_substep(int grid, int bs, cudaStream_t st, const PModel<R_>& M, int n, R_* q, R_* dq, const R_* tau, const R_* fext,
-                      int lcp_mode, int pgs_iters, const ContactSink<R_>& sink) {
+                      int lcp_mode, int pgs_iters, const ContactSink<R_>& sink, const R_*) {
     k_substep<T_, R_><<<grid, bs, 0, st>>>(M, n, q, dq, tau, fext, lcp_mode, pgs_iters, sink);
 }
 // lane-cooperative kernels: 4 warps per block, Coop<T>::WPW worlds per warp

@@ -490,7 +490,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     for (int f = 0; f < K.frame_skip; f++) {
         const ContactSink<R>* sk = (active && f == K.frame_skip - 1 && a.sink.count) ? &a.sink : nullptr;
         substep_loop<R>(M, q, dq, tau, false, tau, tau, tau, K.fluid_force != 0, K.fluid_offset, K.fluid_coef, a.lcp_mode,
-                        a.pgs_iters, sk, w);
+                        a.pgs_iters, sk, w, (a.wpar && active) ? a.wpar + w : nullptr, (size_t)a.n);
     }
     if (K.kind != DARTB_TASK_LOCOMOTION) {
         // the contact-free envs: their own reward / done / reset / obs formulas, same TimeLimit and auto-reset plumbing
@@ -608,7 +608,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
 template <typename R>
 __global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const R* tau_in, const R* fext, int lcp_mode,
-               int pgs_iters, const __grid_constant__ ContactSink<R> sink) {
+               int pgs_iters, const __grid_constant__ ContactSink<R> sink, const R* wpar) {
     const int nb = M.nb;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
@@ -630,9 +630,9 @@ k_substep_loop(const __grid_constant__ PModel<R> M, int n, R* qs, R* dqs, const 
             const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
             eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
         }
-        substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, wpar ? wpar + w : nullptr, (size_t)n);
     } else {
-        substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+        substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, wpar ? wpar + w : nullptr, (size_t)n);
     }
     for (int i = 0; i < nb; i++) { qs[(size_t)i * n + w] = q[i]; dqs[(size_t)i * n + w] = dq[i]; }
 }
@@ -644,7 +644,7 @@ struct Launchers {
     void (*step)(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
     void (*reset)(int grid, int bs, size_t shm, cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a);
     void (*substep)(int grid, int bs, cudaStream_t st, const PModel<R>& M, int n, R* q, R* dq, const R* tau, const R* fext,
-                    int lcp_mode, int pgs_iters, const ContactSink<R>& sink);
+                    int lcp_mode, int pgs_iters, const ContactSink<R>& sink, const R* wpar);   // wpar: loop variant only
     // lane-cooperative kernels (planar_coop.cuh); null for the loop variant.  They size their own grid.
     void (*step_coop)(cudaStream_t st, const PModel<R>& M, const PTask<R>& K, const StepArgs<R>& a, const void* lane_table);
     void (*substep_coop)(cudaStream_t st, const PModel<R>& M, const void* lane_table, int n, R* q, R* dq, const R* tau, int lcp_mode,

@@ -409,4 +409,34 @@ static void convert(const PTask<double>& a, PTask<R>& b) {
     }
 }
 
+// Per-world dynamics parameters (dartb_set_body_params): lowers every world's model with its own bodynode masses / friction
+// coefficients ([n][n_bodies], either may be null) and tabulates what the loop kernels read per world:
+// out[(k nb + i) n + w], k = 0..3: mass, cx, cy, izz of planar body i;  out[(4 nb + s) n + w]: friction of capsule s.
+// Returns "" or why a world cannot be lowered to the topology `signature` of the shared model.
+static std::string body_param_table(const dartb_model_t& base, const dartb_task_t& task, int n, const double* mass, const double* mu,
+                                    const std::string& signature, int nb, int ns, std::vector<double>& out) {
+    const int nbd = base.n_bodies;
+    out.assign((size_t)(4 * nb + ns) * n, 0.0);
+    dartb_model_t dm = base;
+    Result res;
+    for (int w = 0; w < n; w++) {
+        for (int i = 0; i < nbd; i++) {
+            if (mass) dm.bodies[i].mass = mass[(size_t)w * nbd + i];
+            if (mu) dm.bodies[i].friction_coeff = mu[(size_t)w * nbd + i];
+        }
+        std::string why = lower_model(dm, task, res);
+        if (!why.empty()) return "world " + std::to_string(w) + " cannot be lowered: " + why;
+        if (res.signature != signature || res.m.nb != nb || res.m.ns != ns)
+            return "world " + std::to_string(w) + " lowers to a different topology";
+        for (int i = 0; i < nb; i++) {
+            out[(size_t)i * n + w] = res.m.mass[i];
+            out[(size_t)(nb + i) * n + w] = res.m.cx[i];
+            out[(size_t)(2 * nb + i) * n + w] = res.m.cy[i];
+            out[(size_t)(3 * nb + i) * n + w] = res.m.izz[i];
+        }
+        for (int k = 0; k < ns; k++) out[(size_t)(4 * nb + k) * n + w] = res.m.smu[k];
+    }
+    return "";
+}
+
 }  // namespace lower

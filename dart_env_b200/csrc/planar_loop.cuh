@@ -46,9 +46,14 @@ DEVI void fk_positions_loop(const PModel<R>& M, const R* q, R* cs, R* sn, R* px,
 template <typename R>
 DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool FEXT, const R* eft, const R* efx,
                        const R* efy, const bool FLUID, R fluid_offset, R fluid_coef, int lcp_mode, int pgs_iters,
-                       const ContactSink<R>* sink, int world) {
+                       const ContactSink<R>* sink, int world, const R* wp = nullptr, size_t wn = 0) {
+    // wp: this world's column of the per-world dynamics parameters (StepArgs::wpar + world, row stride wn) or null
     constexpr int MB = LOOP_MAXB, NR = LOOP_MAXR;
     const int nb = M.nb;
+    auto mass_of = [&](int i) { return wp ? wp[(size_t)i * wn] : M.mass[i]; };
+    auto cx_of = [&](int i) { return wp ? wp[(size_t)(nb + i) * wn] : M.cx[i]; };
+    auto cy_of = [&](int i) { return wp ? wp[(size_t)(2 * nb + i) * wn] : M.cy[i]; };
+    auto izz_of = [&](int i) { return wp ? wp[(size_t)(3 * nb + i) * wn] : M.izz[i]; };
     const R dt = M.dt;
     R th[MB], cs[MB], sn[MB], px[MB], py[MB], rx[MB], ry[MB], wz[MB], vx[MB], vy[MB], ex[MB], ey[MB];
     R s0[MB], s1[MB], s2[MB];  // joint motion subspace in world axes at the body origin: [sgn; uw]
@@ -91,9 +96,9 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
 #pragma unroll 1
     for (int i = nb - 1; i >= 0; i--) {
         const int par = M.parent[i];
-        const R m = M.mass[i];
-        const R dx = cs[i] * M.cx[i] - sn[i] * M.cy[i], dy = sn[i] * M.cx[i] + cs[i] * M.cy[i];
-        const R J = M.izz[i] + m * (dx * dx + dy * dy) + aJ[i], hx = -m * dy + ahx[i], hy = m * dx + ahy[i];
+        const R m = mass_of(i), cxi = cx_of(i), cyi = cy_of(i);
+        const R dx = cs[i] * cxi - sn[i] * cyi, dy = sn[i] * cxi + cs[i] * cyi;
+        const R J = izz_of(i) + m * (dx * dx + dy * dy) + aJ[i], hx = -m * dy + ahx[i], hy = m * dx + ahy[i];
         const R ma = m + ama[i], mb = amb[i], mc = m + amc[i];
         const R Px = m * (vx[i] - wz[i] * dy), Py = m * (vy[i] + wz[i] * dx);
         R pt = vx[i] * Py - vy[i] * Px - (dx * m * M.gy - dy * m * M.gx);
@@ -193,7 +198,7 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
                     depth = rad + (M.ghup - ((lx - M.gcx) * nx + (ly - M.gcy) * ny));
                     Px = lx; Py = ly;
                 }
-                const R mu = M.smu[s];
+                const R mu = wp ? wp[(size_t)(4 * nb + s) * wn] : M.smu[s];
                 const bool fric = mu > (R)DK_FRICTION_THRESHOLD;
                 const R tx = -ny, ty = nx;
                 const int r0 = n;
@@ -257,9 +262,9 @@ DEVI void substep_loop(const PModel<R>& M, R* q, R* dq, const R* tau, const bool
 #pragma unroll 1
         for (int i = nb - 1; i >= 0; i--) {
             const int par = M.parent[i];
-            const R m = M.mass[i];
-            const R dx = cs[i] * M.cx[i] - sn[i] * M.cy[i], dy = sn[i] * M.cx[i] + cs[i] * M.cy[i];
-            const R J = M.izz[i] + m * (dx * dx + dy * dy) + aJ[i], hx = -m * dy + ahx[i], hy = m * dx + ahy[i];
+            const R m = mass_of(i), cxi = cx_of(i), cyi = cy_of(i);
+            const R dx = cs[i] * cxi - sn[i] * cyi, dy = sn[i] * cxi + cs[i] * cyi;
+            const R J = izz_of(i) + m * (dx * dx + dy * dy) + aJ[i], hx = -m * dy + ahx[i], hy = m * dx + ahy[i];
             const R ma = m + ama[i], mb = amb[i], mc = m + amc[i];
             R v0, v1, v2, D;
             if (M.jtype[i] == PM_REV) { const R s = s0[i]; v0 = s * J; v1 = s * hx; v2 = s * hy; D = J; }

@@ -110,6 +110,7 @@ class DartEnv:
         # dart_env.py:54-67: build the world, robot = last skeleton, enforce every limited dof
         self.model = load_model(model_paths[0], dt)
         self.model.enforce_limits()
+        self._skel_frictions = [b.friction_coeff for b in self.model.bodies]   # as loaded, before friction_all
         if friction_all is not None:
             for b in self.model.bodies:
                 b.friction_coeff = float(friction_all)
@@ -270,6 +271,12 @@ class DartEnv:
         v = torch.as_tensor(np.asarray(qvel, dtype=np.float64).reshape(self.num_envs, -1), device=self.engine.device)
         assert q.shape == (self.num_envs, self.model.n_dofs) and v.shape == q.shape
         self.engine.set_state(q.contiguous(), v.contiguous())
+
+    def set_body_params(self, mass=None, friction=None):
+        """`bodynodes[i].set_mass(m)` / `.set_friction_coeff(mu)` per world (snake_7link.py:115-120): arrays
+        [num_envs, n_bodynodes] or None (= the skeleton's value); both None returns to the shared model.  While set, the
+        batch runs on the topology-generic kernels (`engine.kernel_name`)."""
+        self.engine.set_body_params(mass, friction)
 
     def set_state_vector(self, state):
         state = np.asarray(state, dtype=np.float64).reshape(self.num_envs, -1)

@@ -108,6 +108,29 @@ class Engine:
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
         capi.check(self.L.dartb_set_obs_peers(self.h, arr, len(peer_ptrs), int(float_offset)))
 
+    def set_body_params(self, mass=None, friction=None):
+        """Per-world bodynode masses / friction coefficients, numpy [n_worlds, n_bodynodes] each or None (= the model's):
+        `bodynodes[i].set_mass`, `.set_friction_coeff` on single worlds of the batch (snake_7link.py:115-120).  Both None
+        returns to the shared model.  Synchronising; the batch then runs on the loop kernels."""
+        import numpy as np
+        arrs = []
+        for a in (mass, friction):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.ndim != 2 or a.shape[0] != self.n:
+                raise ValueError("expected [n_worlds, n_bodynodes]")
+            if arrs and arrs[0] is not None and arrs[0].shape != a.shape:
+                raise ValueError("mass and friction shapes differ")
+            arrs.append(a)
+        nb = self.nbodies
+        for a in arrs:
+            if a is not None and a.shape[1] != nb:
+                raise ValueError(f"expected [n_worlds, {nb}] (DART bodynode order)")
+        ptr = [a.ctypes.data_as(C.c_void_p) if a is not None else None for a in arrs]
+        capi.check(self.L.dartb_set_body_params(self.h, ptr[0], ptr[1]))
+
     def set_aux(self, aux: torch.Tensor):
         """per-world task state [n, 3] float64 (the reacher's `self.target`, reacher2d.py:7,57-63)"""
         self._chk(aux, (self.n, 3), torch.float64)

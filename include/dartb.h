@@ -212,6 +212,14 @@ int dartb_set_obs_peers(dartb_handle_t h, void* const* d_peers, int32_t n_peers,
 int dartb_set_aux(dartb_handle_t h, const double* d_aux, void* stream);
 int dartb_get_aux(dartb_handle_t h, double* d_aux, void* stream);
 
+/* Per-world dynamics parameters (the dynamics randomisation of snake_7link.py:20-25,115-120 —
+ * bodynodes[i].set_mass(m), bodynodes[i].set_friction_coeff(mu) on one world of the batch).  h_mass / h_friction are HOST
+ * arrays [n_worlds, model.n_bodies] in DART bodynode order (either may be NULL = the model's values; both NULL returns the
+ * engine to the shared model).  set_mass keeps the body's moment of inertia (DART 6 Inertia::setMass); a contact's friction
+ * is min(body, ground) as in the shared model.  Synchronises the device; while per-world parameters are set the batch runs
+ * on the topology-generic loop kernels, the only ones that read them (dartb_kernel_name reports "loop:generic"). */
+int dartb_set_body_params(dartb_handle_t h, const double* h_mass, const double* h_friction);
+
 /* world.collision_result.contacts of the LAST sub-step (walker2d.py:38-41).
  * d_count int32[n]; d_body int32[n, max_contacts] (robot body index per contact, -1 padded,
  * ordered by collision-shape index); d_data float[n, max_contacts, 10] =

@@ -298,9 +298,11 @@ void orc_set_option(orc_world_t* w, int key, double val) {
     else if (key == DARTB_OPT_FRICTION_ALL)
         for (int i = 0; i < w->nb; i++) w->m.bodies[i].friction_coeff = val;
 }
-void orc_set_mass(orc_world_t* w, int body, double mass) { /* bn.set_mass (snake_7link.py:117) */
-    double old = w->m.bodies[body].mass;
-    if (old > 0) for (int k = 0; k < 9; k++) w->m.bodies[body].inertia[k] *= mass / old;
+void orc_set_mass(orc_world_t* w, int body, double mass) {
+    /* bn.set_mass (snake_7link.py:117) -> DART 6 BodyNode::setMass -> Inertia::setMass: the mass changes, the moment of
+     * inertia about the COM (the <moment_of_inertia> of the .skel, or the shape-derived one computed at load) stays, and
+     * the spatial tensor is rebuilt from both (DART is a pydart2 dependency absent from the reference tree: published
+     * behaviour restated) */
     w->m.bodies[body].mass = mass;
     build_constants(w);
 }

@@ -312,3 +312,80 @@ def test_fused_obs_gather_peer_stores(variant, n):
     torch.cuda.synchronize()
     assert (peers[0] == -7.0).all()
     eng.close()
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_per_world_body_params_match_oracle(f64):
+    """SURVEY 8f.2 dynamics randomisation (snake_7link.py:115-120: bodynodes[i].set_mass / set_friction_coeff): with
+    dartb_set_body_params every world steps with ITS masses and friction coefficients — compared, world by world, with an
+    oracle world that had orc_set_mass / orc_set_friction applied; clearing returns to the shared model and its kernel."""
+    from oracle import oracle as orc
+    env_id = "DartWalker2d-v1"
+    g = np.load(os.path.join(GOLD, "walker2d.npz"))
+    idx = np.concatenate([np.where(g["sub_ncontact"] > 0)[0][:40], np.arange(24)])
+    n = len(idx)
+    env = _make(env_id, num_envs=n, output="numpy", seed=0, auto_reset=False, f64=f64)
+    auto_name = env.engine.kernel_name
+    nb = len(env.model.bodies)
+    rng = np.random.RandomState(11)
+    mass0 = np.array([b.mass for b in env.model.bodies])
+    fr0 = np.array([b.friction_coeff for b in env.model.bodies])
+    mass = np.clip(mass0 + rng.uniform(-1.5, 1.5, (n, nb)), 0.05, None)
+    fric = np.clip(fr0 + rng.uniform(-0.5, 0.5, (n, nb)), 0.0, None)
+    env.set_body_params(mass, fric)
+    assert "loop:generic" in env.engine.kernel_name
+    env.set_state(g["sub_q"][idx], g["sub_dq"][idx])
+    env.do_simulation(g["sub_tau"][idx], 1)
+    s = env.state_vector()
+    nd = env.model.n_dofs
+    worst = 0.0
+    for k, i in enumerate(idx):
+        w = orc.OracleWorld(env.model)
+        for b in range(nb):
+            w.set_mass(b, mass[k, b]); w.set_friction(b, fric[k, b])
+        w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+        oq, odq = w.get_state()
+        if not f64 and (g["sub_contact_margin"][i] < 1e-4 or g["sub_limit_margin"][i] < 1e-4 or g["sub_tie_margin"][i] < 1e-4):
+            continue   # the golden's tagged event-margin samples (fp32 can take the other side of a threshold)
+        worst = max(worst, float((np.abs(s[k, nd:] - odq) / (1 + np.abs(odq))).max()), float(np.abs(s[k, :nd] - oq).max()))
+    assert worst < (1e-8 if f64 else 5e-4), worst   # (the CPU build of the same kernel source stays below 1e-4 on these samples)
+    # the fused env.step() reads the same table
+    env.set_state(g["sub_q"][idx], g["sub_dq"][idx])
+    ob, rew, done, _ = env.step(np.zeros((n, env.act_dim), dtype=np.float32))
+    assert np.isfinite(ob).all() and np.isfinite(rew).all()
+    # both None: back to the shared model on the automatically chosen kernel, bit-identical to a fresh env
+    env.set_body_params(None, None)
+    assert env.engine.kernel_name == auto_name
+    env2 = _make(env_id, num_envs=n, output="numpy", seed=0, auto_reset=False, f64=f64)
+    for e in (env, env2):
+        e.set_state(g["sub_q"][idx], g["sub_dq"][idx])
+        e.do_simulation(g["sub_tau"][idx], 1)
+    assert np.array_equal(env.state_vector(), env2.state_vector())
+    # bad input fails loudly and leaves the engine usable
+    from dart_env_b200.capi import DartbError
+    with pytest.raises(DartbError):
+        env.set_body_params(-np.ones((n, nb)), None)
+    env.do_simulation(g["sub_tau"][idx], 1)
+    env.close(); env2.close()
+
+
+def test_snake_randomize_dynamics_flag():
+    """snake_7link.py:11,20-25,115-120: `randomize_dynamics` (hard-coded off in the reference) redraws every bodynode's
+    mass / friction at reset — here one draw per world.  Identically seeded worlds then diverge only through their masses."""
+    from dart_env_b200.envs import DartSnake7LinkEnv
+    n = 64
+    a = np.random.RandomState(0).uniform(-1, 1, (10, 1, 6)).astype(np.float32).repeat(n, 1)
+    outs = []
+    for rd in (False, True):
+        env = DartSnake7LinkEnv(num_envs=n, output="numpy", seed=0, auto_reset=False, randomize_dynamics=rd)
+        env.seed([7] * n)            # every world draws the same reset noise
+        np.random.seed(3)
+        ob = env.reset()
+        assert ("loop:generic" in env.engine.kernel_name) == rd
+        for t in range(10):
+            ob, rew, done, _ = env.step(a[t])
+        assert np.isfinite(ob).all()
+        outs.append(ob.copy())
+        env.close()
+    assert np.abs(outs[0] - outs[0][0]).max() == 0.0          # shared model: identical worlds stay identical
+    assert np.abs(outs[1] - outs[1][0]).max() > 1e-3           # per-world masses: they do not

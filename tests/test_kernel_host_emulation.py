@@ -303,3 +303,40 @@ def test_quad_kernel_world_independent_of_warp_neighbours(models):
         mixed = np.array([v for pair in zip(small, np.resize(big, 8)) for v in pair])
         _, _, (qm, dqm, *_r) = _run_quad(models, env_id, f64, idx=mixed)
         assert np.array_equal(qa, qm[0::2]) and np.array_equal(dqa, dqm[0::2])
+
+
+# ------------------------------------------------------------------------ per-world dynamics parameters
+@pytest.mark.parametrize("env_id", ["DartWalker2d-v1", "DartSnake7Link-v1", "DartHalfCheetah-v1"])
+def test_per_world_body_params_equal_oracle_set_mass_set_friction(models, env_id):
+    """bodynodes[i].set_mass / set_friction_coeff per world (snake_7link.py:115-120): the loop kernel reading the table
+    dartb_set_body_params uploads == one oracle world per sample with orc_set_mass / orc_set_friction applied."""
+    from oracle import oracle as orc
+    g = np.load(os.path.join(GOLD, FILES[env_id]))
+    has_c = np.where(g["sub_ncontact"] > 0)[0][:12]
+    idx = np.concatenate([has_c, np.arange(8)]) if len(has_c) else np.arange(16)
+    m = models[env_id]
+    nb = len(m.bodies)
+    rng = np.random.RandomState(5)
+    mass0 = np.array([b.mass for b in m.bodies])
+    fr0 = np.array([b.friction_coeff for b in m.bodies])
+    mass = np.clip(mass0 + rng.uniform(-1.5, 1.5, (len(idx), nb)), 0.0, None) * (mass0 > 0)   # massless helper bodies stay massless
+    fric = np.clip(fr0 + rng.uniform(-0.5, 0.5, (len(idx), nb)), 0.0, None)
+    ref = []
+    for k, i in enumerate(idx):
+        w = orc.OracleWorld(m)
+        for b in range(nb):
+            w.set_mass(b, mass[k, b]); w.set_friction(b, fric[k, b])
+        w.set_state(g["sub_q"][i], g["sub_dq"][i]); w.set_forces(g["sub_tau"][i]); w.step()
+        ref.append(np.concatenate(w.get_state()))
+    ref = np.array(ref)
+    q2, dq2, *_ = emu.substep_body_params(m, SPECS[env_id].task, g["sub_q"][idx], g["sub_dq"][idx], g["sub_tau"][idx],
+                                          mass=mass, friction=fric, f64=True)
+    got = np.concatenate([q2, dq2], 1)
+    assert np.allclose(got, ref, rtol=1e-7, atol=1e-7), np.abs(got - ref).max()
+    # and the parameters matter: the shared-model step differs
+    q0, dq0, *_ = emu.substep(m, SPECS[env_id].task, g["sub_q"][idx], g["sub_dq"][idx], g["sub_tau"][idx], f64=True, variant=1)
+    assert np.abs(dq0 - dq2).max() > 1e-3
+    # mass only / friction only go through the same table
+    q3, dq3, *_ = emu.substep_body_params(m, SPECS[env_id].task, g["sub_q"][idx], g["sub_dq"][idx], g["sub_tau"][idx],
+                                          mass=np.tile(mass0, (len(idx), 1)), friction=None, f64=True)
+    assert np.allclose(dq3, dq0, rtol=1e-12, atol=1e-12)

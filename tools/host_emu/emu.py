@@ -46,6 +46,27 @@ def substep(model, task, q, dq, tau=None, fext=None, f64=False, lcp_mode=0, pgs_
     return q2, dq2, cnt, body, data
 
 
+def substep_body_params(model, task, q, dq, tau=None, mass=None, friction=None, f64=False, lcp_mode=0, pgs_iters=30, maxc=8):
+    """One sub-step of the loop kernel with per-world bodynode masses / friction coefficients [n, n_bodies]."""
+    L = lib()
+    cm, ct = pack_model(model), pack_task(task)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    dq = np.ascontiguousarray(dq, dtype=np.float64)
+    n, nd = q.shape
+    dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+    tau, mass, friction = (None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (tau, mass, friction))
+    q2, dq2 = np.zeros_like(q), np.zeros_like(dq)
+    cnt = np.zeros(n, dtype=np.int32)
+    body = -np.ones((n, maxc), dtype=np.int32)
+    data = np.zeros((n, maxc, 10), dtype=np.float32)
+    rc = L.emu_substep_body_params(C.byref(cm), C.byref(ct), int(f64), n, dp(q), dp(dq), dp(tau), dp(mass), dp(friction),
+                                   lcp_mode, pgs_iters, dp(q2), dp(dq2), cnt.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   body.ctypes.data_as(C.POINTER(C.c_int32)), data.ctypes.data_as(C.POINTER(C.c_float)), maxc)
+    if rc:
+        raise RuntimeError(L.emu_last_error().decode())
+    return q2, dq2, cnt, body, data
+
+
 def lcp(A, b, lo, hi, findex, mode=0, f64=True):
     """Kernel-source LCP solvers on the CPU (mode: 0 dispatch, 1 small<8>, 2 bpp_local, 3 dantzig,
     4 small<4>, 5 small<6>).  Returns (x, failed)."""

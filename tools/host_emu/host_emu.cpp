@@ -44,9 +44,10 @@ static void run_substep(const PModel<R>& M, int n, const double* q_in, const dou
 template <typename R>
 static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, const double* dq_in, const double* tau_in,
                              const double* fext, int lcp_mode, int pgs_iters, double* q_out, double* dq_out,
-                             int32_t* count, int32_t* body, float* data, int maxc) {
+                             int32_t* count, int32_t* body, float* data, int maxc, const R* wpar = nullptr) {
     const int NB = M.nb;
     for (int w = 0; w < n; w++) {
+        const R* wp = wpar ? wpar + w : nullptr;
         R q[LOOP_MAXB], dq[LOOP_MAXB], tau[LOOP_MAXB], eft[LOOP_MAXB], efx[LOOP_MAXB], efy[LOOP_MAXB];
         for (int i = 0; i < NB; i++) { q[i] = (R)q_in[w * NB + i]; dq[i] = (R)dq_in[w * NB + i]; tau[i] = tau_in ? (R)tau_in[w * NB + i] : (R)0; eft[i] = efx[i] = efy[i] = 0; }
         ContactSink<R> sink;
@@ -62,9 +63,9 @@ static void run_substep_loop(const PModel<R>& M, int n, const double* q_in, cons
                 const R ox = cs[g] * M.dox[k] - sn[g] * M.doy[k], oy = sn[g] * M.dox[k] + cs[g] * M.doy[k];
                 eft[g] += ox * fy - oy * fx; efx[g] += fx; efy[g] += fy;
             }
-            substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+            substep_loop<R>(M, q, dq, tau, true, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, wp, (size_t)n);
         } else {
-            substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w);
+            substep_loop<R>(M, q, dq, tau, false, eft, efx, efy, false, (R)0, (R)0, lcp_mode, pgs_iters, &sink, w, wp, (size_t)n);
         }
         for (int i = 0; i < NB; i++) { q_out[w * NB + i] = (double)q[i]; dq_out[w * NB + i] = (double)dq[i]; }
     }
@@ -134,6 +135,28 @@ extern "C" void emu_counters(long* out, int reset) { for (int i = 0; i < 8; i++)
 static std::string g_err;
 
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
+
+// the loop kernel's sub-step with per-world bodynode masses / friction coefficients ([n][n_bodies], either may be null):
+// the same lower::body_param_table dartb_set_body_params uploads
+extern "C" int emu_substep_body_params(const dartb_model_t* model, const dartb_task_t* task, int f64, int n, const double* q,
+                                       const double* dq, const double* tau, const double* mass, const double* mu, int lcp_mode,
+                                       int pgs_iters, double* q_out, double* dq_out, int32_t* count, int32_t* body, float* data,
+                                       int maxc) {
+    lower::Result res;
+    std::string why = lower::lower_model(*model, *task, res);
+    if (!why.empty()) { g_err = why; return 1; }
+    std::vector<double> tab;
+    why = lower::body_param_table(*model, *task, n, mass, mu, res.signature, res.m.nb, res.m.ns, tab);
+    if (!why.empty()) { g_err = why; return 1; }
+    if (f64) run_substep_loop<double>(res.m, n, q, dq, tau, nullptr, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, tab.data());
+    else {
+        PModel<float> mf;
+        lower::convert(res.m, mf);
+        std::vector<float> tf(tab.begin(), tab.end());
+        run_substep_loop<float>(mf, n, q, dq, tau, nullptr, lcp_mode, pgs_iters, q_out, dq_out, count, body, data, maxc, tf.data());
+    }
+    return 0;
+}
 
 // returns 0 ok; arrays are [n, nd] row-major doubles (converted to the kernel precision inside)
 extern "C" int emu_substep(const dartb_model_t* model, const dartb_task_t* task, int f64, int n, const double* q,
