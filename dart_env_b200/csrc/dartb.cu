@@ -150,8 +150,13 @@ static int lower_into(dartb_engine* e) {
         //   (crossovers, r2i_xover.log)  Hopper 2048: coop 32.5, quad 34.2; 3072: quad 34.5, coop 36.7; 10240: static 50.3, quad 65.1
         //   Walker2d 2048: coop 54.5, quad 73.5; 3072: 80.1 / 79.6; 10240: static 130, quad 140   HalfCheetah 10240: coop 369, static 419;
         //   12288: 438 / 441   Snake7Link 1024: quad 27.2, coop 28.9; 12288: static 45.2, quad 53.9
-        if (lim_coop < 0) lim_coop = topo == TOPO_HOPPER ? 2560 : (topo == TOPO_WALKER ? 2560 : (topo == TOPO_CHEETAH ? 12288 : 592));
-        if (lim_quad < 0) lim_quad = topo == TOPO_HOPPER ? 8880 : (topo == TOPO_WALKER ? 8880 : (topo == TOPO_CHEETAH ? 0 : 8880));
+        //   after the branch-free solvers (r2p_sweep.log; coop / quad / static):  Hopper 1536: 30.0 / 30.4; 2048: 30.9 / 30.7; 2560: 33.3 / 30.7;
+        //   8192: - / 37.5 / 41.0; 10240: - / 59.4 / 41.6   Walker2d 2048: 51.9 / 63.0; 2560: 69.3 / 66.8; 3072: 76.3 / 69.4; 8192: - / 102 / 122;
+        //   10240: - / 129 / 115   HalfCheetah 8192: 286 / 346 / 399; 10240: 349 / 371 / 394; 12288: 414 / 401 / 416; 16384: 549 / 464 / 458
+        //   Snake7Link 512: 27.0 / 24.9; 768: 27.1 / 25.3; 8192: - / 35.0 / 41.5; 12288: - / 51.9 / 42.2
+        //   (the quad form steps up past 8880 worlds = one wave of 148 x 60 worlds, the 16-lane cooperative form past 2368)
+        if (lim_coop < 0) lim_coop = topo == TOPO_HOPPER ? 2048 : (topo == TOPO_WALKER ? 2368 : (topo == TOPO_CHEETAH ? 11264 : 448));
+        if (lim_quad < 0) lim_quad = topo == TOPO_HOPPER ? 8880 : (topo == TOPO_WALKER ? 8880 : (topo == TOPO_CHEETAH ? 13312 : 8880));
         if (e->lcp_mode == 1) lim_quad = 0;
         e->variant = (e->n <= lim_coop) ? 2 : ((e->n <= lim_quad) ? 3 : 0);
     }

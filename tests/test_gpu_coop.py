@@ -66,8 +66,8 @@ def test_automatic_kernel_choice_by_batch_size(models):
     try:
         for env_id, sizes in (("DartHopper-v1", ((2048, "coop:"), (4096, "quad:"), (16384, "static:"))),
                               ("DartWalker2d-v1", ((2048, "coop:"), (8192, "quad:"), (16384, "static:"))),
-                              ("DartHalfCheetah-v1", ((4096, "coop:"), (16384, "static:"))),
-                              ("DartSnake7Link-v1", ((512, "coop:"), (4096, "quad:"), (32768, "static:")))):
+                              ("DartHalfCheetah-v1", ((4096, "coop:"), (12288, "quad:"), (16384, "static:"))),
+                              ("DartSnake7Link-v1", ((256, "coop:"), (4096, "quad:"), (32768, "static:")))):
             ref = None
             for n, tag in sizes:
                 e = P._engine(models, env_id, n, seed=1)

@@ -122,6 +122,14 @@ elif mode == "r2final":   # the automatic choice at every config size, exact and
         cfgs.append((env_id, n, "128", "-1", "30"))
     for env_id, n, v in (("DartHopper-v1", 4096, "2"), ("DartHopper-v1", 4096, "0"), ("DartWalker2d-v1", 4096, "2"), ("DartHalfCheetah-v1", 8192, "3"), ("DartWalker2d-v1", 16384, "3")):
         cfgs.append((env_id, n, "128", v))
+elif mode == "r2p":   # after the branch-free solvers: the forms around every automatic crossover again, and the loop kernel
+    for env_id, sizes in (("DartHopper-v1", (1536, 2048, 2560, 3072, 8192, 10240, 12288)), ("DartWalker2d-v1", (1536, 2048, 2560, 3072, 8192, 10240, 12288)),
+                          ("DartHalfCheetah-v1", (8192, 10240, 12288, 16384)), ("DartSnake7Link-v1", (512, 768, 8192, 12288, 16384))):
+        for n in sizes:
+            for v in (("2", "3") if n <= 3072 else (("0", "3") if env_id != "DartHalfCheetah-v1" else ("0", "2", "3"))):
+                cfgs.append((env_id, n, "128", v))
+    for env_id, n in (("DartHopper-v1", 4096), ("DartWalker2d-v1", 4096), ("DartSnake7Link-v1", 4096), ("DartHalfCheetah-v1", 4096)):
+        cfgs.append((env_id, n, "128", "1"))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
