@@ -111,6 +111,7 @@ class DartEnv:
         self.model = load_model(model_paths[0], dt)
         self.model.enforce_limits()
         self._skel_frictions = [b.friction_coeff for b in self.model.bodies]   # as loaded, before friction_all
+        self._body_mass = self._body_mu = None   # per-world bodynode parameters (set_body_params), None = the model's
         if friction_all is not None:
             for b in self.model.bodies:
                 b.friction_coeff = float(friction_all)
@@ -276,7 +277,17 @@ class DartEnv:
         """`bodynodes[i].set_mass(m)` / `.set_friction_coeff(mu)` per world (snake_7link.py:115-120): arrays
         [num_envs, n_bodynodes] or None (= the skeleton's value); both None returns to the shared model.  While set, the
         batch runs on the topology-generic kernels (`engine.kernel_name`)."""
+        mass = None if mass is None else np.array(mass, dtype=np.float64).reshape(self.num_envs, -1)
+        friction = None if friction is None else np.array(friction, dtype=np.float64).reshape(self.num_envs, -1)
         self.engine.set_body_params(mass, friction)
+        self._body_mass, self._body_mu = mass, friction
+
+    def _body_param_array(self, which):
+        cur = self._body_mass if which == "mass" else self._body_mu
+        if cur is not None:
+            return cur.copy()
+        vals = [b.mass if which == "mass" else b.friction_coeff for b in self.model.bodies]
+        return np.tile(np.asarray(vals, dtype=np.float64), (self.num_envs, 1))
 
     def set_state_vector(self, state):
         state = np.asarray(state, dtype=np.float64).reshape(self.num_envs, -1)

@@ -54,11 +54,29 @@ class BodyNodeView:
         a = t.cpu().numpy()
         return a if self.skel.env.batched else a[0]
 
-    @property
-    def m(self) -> float:
-        return float(self._b.mass)
+    def mass(self):
+        """bn.mass() (snake_7link.py:24): a float, or the per-world array once set_mass gave the worlds different masses"""
+        pw = self.skel.env._body_mass
+        if pw is None:
+            return float(self._b.mass)
+        col = pw[:, self.id]
+        return float(col[0]) if (col == col[0]).all() else col.copy()
 
-    mass = m
+    m = property(mass)
+
+    def set_mass(self, mass):
+        """bn.set_mass(m) (snake_7link.py:117): a scalar for every world of the batch, or one value per world"""
+        env = self.skel.env
+        M = env._body_param_array("mass")
+        M[:, self.id] = mass
+        env.set_body_params(M, env._body_mu)
+
+    def set_friction_coeff(self, mu):
+        """bn.set_friction_coeff(mu) (snake_7link.py:30,119): a scalar for every world, or one value per world"""
+        env = self.skel.env
+        F = env._body_param_array("friction")
+        F[:, self.id] = mu
+        env.set_body_params(env._body_mass, F)
 
     def local_com(self) -> np.ndarray:
         return np.array(self._b.com, dtype=np.float64)
@@ -90,8 +108,12 @@ class BodyNodeView:
 
     dC = property(com_linear_velocity)
 
-    def friction_coeff(self) -> float:
-        return float(self._b.friction_coeff)
+    def friction_coeff(self):
+        pw = self.skel.env._body_mu
+        if pw is None:
+            return float(self._b.friction_coeff)
+        col = pw[:, self.id]
+        return float(col[0]) if (col == col[0]).all() else col.copy()
 
 
 class DofView:

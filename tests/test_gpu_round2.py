@@ -389,3 +389,35 @@ def test_snake_randomize_dynamics_flag():
         env.close()
     assert np.abs(outs[0] - outs[0][0]).max() == 0.0          # shared model: identical worlds stay identical
     assert np.abs(outs[1] - outs[1][0]).max() > 1e-3           # per-world masses: they do not
+
+
+def test_bodynode_views_set_mass_and_friction():
+    """the pydart2 spellings the reference uses (snake_7link.py:24-25,117-120): bn.mass(), bn.friction_coeff(),
+    bn.set_mass(m), bn.set_friction_coeff(mu) — a scalar reaches every world, an array one world each"""
+    n = 16
+    env = _make("DartHopper-v1", num_envs=n, output="numpy", seed=0, auto_reset=False, f64=True)
+    bn = env.robot_skeleton.bodynodes[3]
+    m0, f0 = bn.mass(), bn.friction_coeff()
+    assert isinstance(m0, float) and isinstance(f0, float) and bn.m == m0
+    env.reset()
+    s0 = env.state_vector().copy()
+    tau = np.zeros((n, env.model.n_dofs)); tau[:, 3:] = 30.0
+    env.do_simulation(tau, 4)
+    base = env.state_vector().copy()
+    bn.set_mass(m0 + 1.0)
+    assert bn.mass() == m0 + 1.0 and "loop:generic" in env.engine.kernel_name
+    env.set_state_vector(s0); env.do_simulation(tau, 4)
+    heavier = env.state_vector().copy()
+    assert np.abs(heavier - base).max() > 1e-4
+    per_world = m0 + np.linspace(0.0, 1.0, n)
+    bn.set_mass(per_world)
+    assert np.array_equal(bn.mass(), per_world)
+    env.set_state_vector(s0); env.do_simulation(tau, 4)
+    s = env.state_vector()
+    assert np.allclose(s[0], base[0], rtol=1e-9, atol=1e-9)        # world 0 kept the original mass: same as the compiled kernel, fp64
+    assert np.allclose(s[-1], heavier[-1], rtol=1e-12, atol=1e-12)   # world n-1 has m0 + 1
+    bn.set_friction_coeff(0.25)
+    assert bn.friction_coeff() == 0.25 and np.array_equal(bn.mass(), per_world)
+    env.set_body_params(None, None)
+    assert bn.mass() == m0 and bn.friction_coeff() == f0 and "loop:generic" not in env.engine.kernel_name
+    env.close()
