@@ -120,7 +120,34 @@ __host__ __device__ constexpr bool topo_is_ancestor(int j, int b) {  // j == b o
 // ------------------------------------------------------------------------ scalar helpers
 template <typename R> struct Num;
 template <> struct Num<float> {
+#ifdef DARTB_LIBM_SINCOS
     static DEVI void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+#else
+    // Branch-free: Cody-Waite reduction by pi/2 in three fma steps (pi/2 split into three floats), then the minimax
+    // polynomials of sin and cos on [-pi/4, pi/4] and quadrant selects.  libm's sincosf carries a Payne-Hanek slow path for
+    // |x| > 105615 that joint angles never reach (137 static branches per inlined copy; the hottest source line of the
+    // headline capture, profiles/r2_hopper_quad_v2).  Max error 1.5 ulp / 7e-8 absolute for |x| <= 1e5 (libm: 2 ulp); the
+    // same instructions on the CPU build, so the emulation is bit-identical here.
+    static DEVI void sincos_(float x, float* s, float* c) {
+        const float k = rintf(x * 6.366197467e-01f);
+        float r = fmaf(k, -1.5707963705062866f, x);
+        r = fmaf(k, 4.371138828673793e-08f, r);
+        r = fmaf(k, 1.7151245100058819e-15f, r);
+        const int q = (int)k;
+        const float r2 = r * r;
+        float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+        ps = fmaf(ps, r2, -1.6666654611e-1f);
+        const float sn = fmaf(ps * r2, r, r);
+        float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+        pc = fmaf(pc, r2, 4.166664568298827e-2f);
+        pc = fmaf(pc, r2, -0.5f);
+        const float cs = fmaf(pc, r2, 1.0f);
+        const bool sw = (q & 1) != 0;
+        const float so = sw ? cs : sn, co = sw ? sn : cs;
+        *s = (q & 2) ? -so : so;
+        *c = ((q + 1) & 2) ? -co : co;
+    }
+#endif
     static DEVI float sqrt_(float x) { return sqrtf(x); }
     static DEVI float rsqrt_(float x) { return rsqrtf(x); }   // MUFU.RSQ, 2 ulp: inner solves of the LCP only
     // 1/x of the projected articulated inertias (12 per DART step): one MUFU.RCP (max rel. error
