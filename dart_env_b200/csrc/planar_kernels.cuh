@@ -149,6 +149,14 @@ template <> struct Num<float> {
     }
 #endif
     static DEVI float sqrt_(float x) { return sqrtf(x); }
+    // sqrt of the diagonal scales in the LCP's tolerance tests (tw = tol * (|b| + sqrt(A_ii) * S)): one MUFU-based
+    // approximation (max rel. error 2^-22) instead of the IEEE sequence with its slow-path branch — sqrtf was the hottest
+    // source line of the HalfCheetah capture (profiles/r2_cheetah16k_v2: 4.2 % of the samples)
+#ifdef DARTB_HOST_EMU
+    static DEVI float sqrt_tol_(float x) { return sqrtf(x); }
+#else
+    static DEVI float sqrt_tol_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
     static DEVI float rsqrt_(float x) { return rsqrtf(x); }   // MUFU.RSQ, 2 ulp: inner solves of the LCP only
     // 1/x of the projected articulated inertias (12 per DART step): one MUFU.RCP (max rel. error
     // 2^-23) instead of the IEEE sequence with its slow-path branch
@@ -178,6 +186,7 @@ template <> struct Num<float> {
 template <> struct Num<double> {
     static DEVI void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
     static DEVI double sqrt_(double x) { return sqrt(x); }
+    static DEVI double sqrt_tol_(double x) { return sqrt(x); }
     static DEVI double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static DEVI double rcp_(double x) { return 1.0 / x; }
     static DEVI double abs_(double x) { return fabs(x); }
@@ -466,7 +475,7 @@ DEVI bool lcp_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
     // tolerance a degenerate row (x at its bound AND w = 0) flips between sets forever in fp32.
     R sd[NM];
 #pragma unroll
-    for (int i = 0; i < NM; i++) sd[i] = Num<R>::sqrt_(A[i][i]);
+    for (int i = 0; i < NM; i++) sd[i] = Num<R>::sqrt_tol_(A[i][i]);
 #pragma unroll 1
     for (int stage = 0; stage < 2; stage++) {
         if (stage == 1) {
@@ -634,7 +643,7 @@ DEVI bool lcp_ppt(int n, const R* Ag, R* xg, const R* bg, const R* log_, const R
         x[i] = 0;
 #pragma unroll
         for (int j = 0; j < NM; j++) T[i][j] = (on && j < n) ? Ag[i * n + j] : (i == j ? (R)1 : (R)0);
-        sd[i] = Num<R>::sqrt_(T[i][i]);
+        sd[i] = Num<R>::sqrt_tol_(T[i][i]);
         // initial set = the solution of the decoupled (diagonal) problem (see lcp_small)
         unsigned s = 0, c = 3;
         if (!on || !(T[i][i] > Num<R>::inert())) s = 3;            // padding / inert row
@@ -839,7 +848,7 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
             uint64_t nst = st;
             int nbad = 0, last = -1;
             R xs = 0, S = 0;
-            for (int i = 0; i < n; i++) { const R ax = Num<R>::abs_(x[i]); xs = ax > xs ? ax : xs; S += Num<R>::sqrt_(A[i * n + i]) * ax; }
+            for (int i = 0; i < n; i++) { const R ax = Num<R>::abs_(x[i]); xs = ax > xs ? ax : xs; S += Num<R>::sqrt_tol_(A[i * n + i]) * ax; }
             const R tx = Num<R>::lcp_tol() * xs;
             for (int i = 0; i < n; i++) {
                 const unsigned si = (unsigned)(st >> (2 * i)) & 3u;
@@ -853,7 +862,7 @@ DEVI bool lcp_bpp_local(int n, const R* A, R* x, const R* b, const R* lo_in, con
 #pragma unroll 4
                     for (int j = 0; j < n; j++) w += A[i * n + j] * x[j];
                     EMU_COUNT(7, n);
-                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + Num<R>::sqrt_(A[i * n + i]) * S);
+                    const R tw = Num<R>::lcp_tol() * (Num<R>::abs_(b[i]) + Num<R>::sqrt_tol_(A[i * n + i]) * S);
                     if (((si == 1 && w < -tw) || (si == 2 && w > tw)) && lo[i] < hi[i]) { nbad++; last = i; nst = nst & clr; }
                 }
             }
@@ -890,7 +899,7 @@ DEVI bool lcp_ppt_loop(int n, const R* A, R* x, const R* b, const R* lo_in, cons
 #pragma unroll 1
         for (int j = 0; j < n; j++) T[i * n + j] = A[i * n + j];
         const R d = A[i * n + i];
-        sd[i] = Num<R>::sqrt_(d);
+        sd[i] = Num<R>::sqrt_tol_(d);
         unsigned s = 0, c = 3;
         if (!(d > Num<R>::inert())) s = 3;                            // inert row
         else if (fidx[i] >= 0) s = 3;                                  // friction rows wait for stage 2

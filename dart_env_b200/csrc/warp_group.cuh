@@ -121,7 +121,7 @@ struct GroupLcp {
                 Tb[h][cc] = (valid[h] && cc < n) ? A[h][cc] : (cc == r ? (R)1 : (R)0);
                 if (cc == r) diag = Tb[h][cc];
             }
-            sd[h] = Num<R>::sqrt_(diag);
+            sd[h] = Num<R>::sqrt_tol_(diag);
             mu[h] = hi[h];
             x[h] = 0;
             fricrow[h] = valid[h] && fi[h] >= 0;

@@ -134,6 +134,12 @@ elif mode == "r2cf":   # the contact-free envs (fused task kinds on the loop ker
     for env_id in ("DartCartPole-v1", "DartCartPoleSwingUp-v1", "DartDoubleInvertedPendulumEnv-v1", "DartReacher-v1"):
         for n in (4096, 65536):
             cfgs.append((env_id, n, "128", "-1"))
+elif mode == "r2s":   # quick A/B set: the automatic choice at the bench sizes
+    for env_id, n in (("DartHopper-v1", 4096), ("DartHopper-v1", 65536), ("DartWalker2d-v1", 4096), ("DartWalker2d-v1", 16384),
+                      ("DartHalfCheetah-v1", 8192), ("DartHalfCheetah-v1", 16384), ("DartSnake7Link-v1", 4096)):
+        cfgs.append((env_id, n, "128", "-1"))
+    for env_id, n in (("DartWalker2d-v1", 16384), ("DartSnake7Link-v1", 4096)):
+        cfgs.append((env_id, n, "128", "-1", "30"))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
