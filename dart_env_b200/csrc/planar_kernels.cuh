@@ -157,7 +157,13 @@ template <> struct Num<float> {
 #else
     static DEVI float sqrt_tol_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
-    static DEVI float rsqrt_(float x) { return rsqrtf(x); }   // MUFU.RSQ, 2 ulp: inner solves of the LCP only
+    // MUFU.RSQ, 2 ulp: inner solves of the LCP only (arguments >= inert(): the flush-to-zero form drops rsqrtf's
+    // denormal pre-/post-scaling, four instructions per call)
+#ifdef DARTB_HOST_EMU
+    static DEVI float rsqrt_(float x) { return rsqrtf(x); }
+#else
+    static DEVI float rsqrt_(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
     // 1/x of the projected articulated inertias (12 per DART step): one MUFU.RCP (max rel. error
     // 2^-23) instead of the IEEE sequence with its slow-path branch
 #ifdef DARTB_HOST_EMU
