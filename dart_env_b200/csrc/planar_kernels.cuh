@@ -1104,7 +1104,7 @@ DEVI void pgs_small(int n, const R* Ag, R* xg, const R* bg, const R* log_, const
 #pragma unroll
         for (int j = 0; j < NM; j++) { A[i][j] = (on && j < n) ? Ag[i * n + j] : (R)0; if (j == i) aii = A[i][j]; }
         const bool live = on && !(aii < (R)1e-9);
-        inv[i] = live ? (R)1 / aii : (R)0;
+        inv[i] = live ? Num<R>::rcp_(aii) : (R)0;   // (one MUFU.RCP: the IEEE division carries a slow-path branch per row)
         if (!live) { lo[i] = 0; hi[i] = 0; }     // padding / inert row (lcp_pgs: aii < 1e-9): the clamp keeps x = 0
     }
     if (!adjacent) { lcp_pgs<R>(n, Ag, xg, bg, log_, hig, fidxg, iters); return; }   // (not produced by this kernel's row layout)

@@ -1,0 +1,29 @@
+#!/bin/bash
+# round-2 session U (final build): what the driver runs at round end — GPU suite, smoke(), both bench arms — plus the launch list
+export DARTB_NO_REBUILD=1
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_errors.log
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2u_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2u_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2u_smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/r2u_smoke.log
+timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 3 > gpurun_out/r2u_bench_ref.log 2>gpurun_out/r2u_bench_ref.err
+timeout 900 python bench.py --gpus 1 --steps 1000 --warmup 50 > gpurun_out/r2u_bench.log 2>gpurun_out/r2u_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_hopper_launches.csv python bench.py --steps 40 --warmup 10 --no-extras > gpurun_out/r2u_launches.log 2>&1
+NCU="ncu --set full --clock-control none --import-source on -k regex:k_env_step -c 1 --launch-skip 25"
+timeout 400 $NCU -o gpurun_out/r2_hopper_quad_v3 -f python bench.py --steps 40 --warmup 10 --no-extras > gpurun_out/r2u_ncu_hopper.log 2>&1
+timeout 400 $NCU -o gpurun_out/r2_walker16k_pgs_v3 -f python bench.py --config 3 --steps 40 --warmup 10 --no-extras > gpurun_out/r2u_ncu_walker.log 2>&1
+timeout 400 $NCU -o gpurun_out/r2_cheetah16k_v3 -f python bench.py --config 4 --steps 40 --warmup 10 --no-extras > gpurun_out/r2u_ncu_cheetah.log 2>&1
+tail -3 gpurun_out/r2u_pytest.log; tail -8 gpurun_out/r2u_smoke.log; python - <<PY
+import json
+r=json.loads([l for l in open('gpurun_out/r2u_bench_ref.log') if l.startswith('{')][-1])
+d=json.loads([l for l in open('gpurun_out/r2u_bench.log') if l.startswith('{')][-1])
+print('reference', r['value'], r['config']['workload'])
+print('ours     ', d['value'], d['config']['workload'], d['kernel'])
+print('us flushed', d['ms_per_step']*1e3, 'warm', d['ms_per_step_l2_warm']*1e3, 'e2e us', d['e2e']['ms_per_step']*1e3, 'e2e value', d['e2e']['value'], 'cpu_baseline', d['cpu_baseline']['value'])
+print('ratio device', d['value']/r['value'], 'e2e', d['e2e']['value']/r['value'], 'same_config', r['config']['workload']==d['config']['workload'])
+print('roofline', {k:d['roofline'][k] for k in ('achieved','peak','frac','traffic','kernel','issue_active_pct','avg_active_lanes') if k in d['roofline']}, d['clocks'], d['gpu_launches'])
+for cid,c in d['configs'].items():
+    print(cid, c['env'], [(x['lcp'], round(x['ms_per_step']*1e3,1), round(x['ms_per_step_l2_warm']*1e3,1), '%.3e'%x['value'], x['roofline']['kernel'], x['roofline'].get('issue_active_pct')) for x in c['runs']], '%.3e'%c['cpu_baseline']['value'])
+print([ (p['pgs_iters'], round(p['us_per_step_l2_warm'],1)) for p in d['configs']['5']['pgs_sweep']])
+PY
