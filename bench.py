@@ -30,6 +30,7 @@ restatement of the reference path (oracle/, "port": pydart2/DART are not install
 host threads for at least 8 s of CPU work regardless of --steps.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -85,6 +86,36 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+class GpuCpuAffinity:
+    """Run the GPU phases on the CPUs NVML names as local to the GPU (nvmlDeviceSetCpuAffinity: the NUMA node the GPU's
+    PCIe root hangs off), like NCCL does for its own threads: the end-to-end step is a launch + sync round trip plus
+    zero-copy PCIe traffic to page-locked memory, both sensitive to a remote socket.  restore() gives the process its
+    full mask back before the CPU baseline runs on all host threads.  BENCH_CPU_AFFINITY=0 switches it off."""
+
+    def __init__(self, torch, local_rank):
+        self.note, self.full = "off", None
+        if os.environ.get("BENCH_CPU_AFFINITY", "1") == "0":
+            return
+        try:
+            import pynvml
+            self.full = os.sched_getaffinity(0)
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            now = os.sched_getaffinity(0)
+            self.note = "nvml ideal cpus: %d of %d" % (len(now), len(self.full))
+        except Exception as e:   # (no NVML / no permission: run unbound and say so)
+            self.note = "unavailable (%s)" % type(e).__name__
+
+    def restore(self):
+        if self.full:
+            try:
+                os.sched_setaffinity(0, self.full)
+            except Exception:
+                pass
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -298,6 +329,7 @@ def run_ours(args, cfg, rank, local_rank, world_size):
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = GpuCpuAffinity(torch, local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
@@ -334,6 +366,11 @@ def run_ours(args, cfg, rank, local_rank, world_size):
     barrier()
     warm_ms = r.timed_warm(K)
     done_frac = r.done_fraction()
+    # (sampled over the two device-timed regions.  It stops HERE: every nvidia-smi query takes driver locks that a kernel
+    # launch waits on, and the end-to-end figure below is wall clock per call — with the 20 ms poll running, one call in
+    # ~350 took milliseconds and the mean moved by 2-30 us from run to run on the same box, gpurun_out/r2v_probe.log)
+    keep_sampler = os.environ.get("BENCH_SAMPLE_DURING_E2E", "0") == "1"   # (A/B switch for the sentence above)
+    clocks = None if keep_sampler else sampler.stop()
 
     # ---- end to end through the public host API (numpy in / numpy out, page-locked output slots)
     henv = make(cfg["env"], num_envs=n, output="numpy", device=local_rank, seed=args.seed, world_offset=rank * n, batched=True)
@@ -345,18 +382,27 @@ def run_ours(args, cfg, rank, local_rank, world_size):
     for i in range(W):
         henv.step(hpool[i % 16])
     barrier()
-    e2e_s = 0.0
     Ke2e = max(K, 200)      # (wall-clock per call: at least 200 calls so that a short --steps run is not one scheduler hiccup)
+    e2e_t = np.empty(Ke2e)
+    # (like `timeit`: the cyclic garbage collector is off inside the timed loop.  A generation-2 pass over the heap torch
+    # leaves behind takes 4-15 ms and lands in one call of ~350 — measured as the whole run-to-run spread of this figure,
+    # 53-71 us around a p50 of 50 us, gpurun_out/r2w_probe.log; the percentiles are reported next to the mean)
+    gc.collect()
+    gc.disable()
     for i in range(Ke2e):
         flush.fill_(float(i & 1))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         o, rw, d, _ = henv.step(hpool[i % 16])
-        e2e_s += time.perf_counter() - t0
+        e2e_t[i] = time.perf_counter() - t0
+    gc.enable()
+    e2e_s = float(e2e_t.sum())   # the figure is the MEAN over every call; the percentiles say how it is distributed
+    e2e_pct = {"p50": float(np.percentile(e2e_t, 50)) * 1e6, "p99": float(np.percentile(e2e_t, 99)) * 1e6, "max": float(e2e_t.max()) * 1e6}
     assert o.dtype == np.float32 and rw.dtype == np.float64 and d.dtype == np.bool_
     h2d, d2h = n * nact * 4, n * nobs * 4 + n * 8 + n
     henv.close()
-    clocks = sampler.stop()   # sampled over all three timed regions (flushed, warm, end-to-end)
+    if keep_sampler:
+        clocks = sampler.stop()
     dev_ms, warm_ms, e2e_s = reduce_max(torch, dist, dev, world_size, (dev_ms, warm_ms, e2e_s))
     total_worlds = n * world_size
     roof = roofline(r, dev_ms / K, peak, peak_src, prof, prof_src) if rank == 0 else None
@@ -413,6 +459,7 @@ def run_ours(args, cfg, rank, local_rank, world_size):
             extras[str(cid)] = out
 
     line = None
+    affinity.restore()   # the CPU baseline runs on every host thread the process was given
     if rank == 0:
         cb, _, _ = cpu_arm(cfg["env"], n, host_threads(), budget_s=10.0)
         if not args.no_extras:
@@ -429,11 +476,12 @@ def run_ours(args, cfg, rank, local_rank, world_size):
                            "actions": "pool of 64 pre-generated U(-1,1) batches per rank, cycled (not regenerated per step)",
                            "l2": "flushed between timed steps (256 MiB write, untimed); working set %.1f MB << L2"
                                  % (algo_bytes(r.nd, nact, nobs) * n / 1e6),
-                           "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks"},
+                           "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                           "cpu_affinity": affinity.note},
                 "value_l2_warm": total_worlds * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
                 "wall_s_timed_loop": t_wall, "done_fraction": done_frac, "kernel": kernel_name,
                 "e2e": {"value": total_worlds * Ke2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_s / Ke2e, "steps": Ke2e,
+                        "ms_per_step": 1e3 * e2e_s / Ke2e, "steps": Ke2e, "us_per_call_rank0": e2e_pct,
                         "api": "DartEnv.step(numpy float32 [N,nact]) -> (float32 obs, float64 rewards, bool dones): one launch + one "
                                "sync; the kernel reads / writes page-locked host memory itself"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "configs": extras}
