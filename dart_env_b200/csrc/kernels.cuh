@@ -90,10 +90,8 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     float* sw = smem + warp * 32 * stage;
 
-    // coalesced action load -> smem [lane][n_act]
-    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
-    __syncwarp();
-
+    // the state loads are issued BEFORE the action staging below waits for its loads (host-facing step: a PCIe round
+    // trip), so that the prologue pays one memory latency, not two
     R q[NB], dq[NB], tau[NB], zero[NB];
     static_for<0, NB>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
@@ -101,6 +99,10 @@ k_env_step(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R>
         dq[i] = active ? a.dq[(size_t)i * a.n + w] : (R)0;
         zero[i] = 0;
     });
+    // coalesced action load -> smem [lane][n_act]
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
+
     // advance(): clamp, scale, scatter (hopper.py:24-32); control cost uses the RAW action
     R a2 = 0;
     if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[lane * K.n_act + j]; a2 += v * v; }
@@ -207,8 +209,7 @@ k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     const bool active = gi < cnt;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     float* sw = smem + warp * WPW * stage;
-    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
-    __syncwarp();
+    // (state and counter loads first, then the action staging: one memory latency for the prologue, see k_env_step)
     R q[NB], dq[NB], tau[NB], zero[NB];
     static_for<0, NB>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
@@ -220,6 +221,8 @@ k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     const int el_in = (active && a.max_episode_steps > 0) ? a.elapsed[w] : 0;
     const uint32_t ep_in = active ? a.episode[w] : 0u;
     uint64_t hint = active ? a.hint[w] : ~(uint64_t)0;
+    if (cnt > 0) for (int k = lane; k < cnt * K.n_act; k += 32) sw[k] = a.action[(size_t)wb * K.n_act + k];
+    __syncwarp();
     R a2 = 0;
     if (active) for (int j = 0; j < K.n_act; j++) { const R v = (R)sw[gi * K.n_act + j]; a2 += v * v; }
     static_for<0, NB>([&](auto ic) {
