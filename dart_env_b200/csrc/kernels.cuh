@@ -16,6 +16,20 @@
 #define DARTB_STEP_MIN_BLOCKS 1
 #endif
 
+// Experiment (DARTB_PREFETCH_PARAMS): touch one word of every 64-byte line of the kernel parameters at entry so that the
+// constant-cache misses of the model overlap instead of being met one by one along K1 / K2 of the first DART step.
+#ifndef DARTB_PREFETCH_PARAMS
+#define DARTB_PREFETCH_PARAMS 0
+#endif
+template <typename S>
+DEVI uint32_t touch_params(const S& s) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(&s);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 4); i += 16) acc |= p[i];
+    return acc;
+}
+
 template <class T, typename R>
 DEVI void write_obs(const PModel<R>& M, const PTask<R>& K, const R (&q)[T::NB], const R (&dq)[T::NB], float* so) {
     constexpr int NB = T::NB;
@@ -209,6 +223,9 @@ k_env_step_quad(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     const bool active = gi < cnt;
     const int stage = K.n_obs > K.n_act ? K.n_obs : K.n_act;
     float* sw = smem + warp * WPW * stage;
+#if DARTB_PREFETCH_PARAMS
+    if ((touch_params(M) | touch_params(K)) == 0x7fc54321u && a.obs) a.obs[0] = 0;   // (never true: keeps the loads)
+#endif
     // (state and counter loads first, then the action staging: one memory latency for the prologue, see k_env_step)
     R q[NB], dq[NB], tau[NB], zero[NB];
     static_for<0, NB>([&](auto ic) {

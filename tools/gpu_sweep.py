@@ -140,6 +140,9 @@ elif mode == "r2s":   # quick A/B set: the automatic choice at the bench sizes
         cfgs.append((env_id, n, "128", "-1"))
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartSnake7Link-v1", 4096)):
         cfgs.append((env_id, n, "128", "-1", "30"))
+elif mode == "r2y":
+    for env_id, n in (("DartHopper-v1", 1024), ("DartHopper-v1", 16384), ("DartWalker2d-v1", 4096), ("DartWalker2d-v1", 16384)):
+        cfgs.append((env_id, n, "128", "-1"))
 elif mode == "r2quadonly":   # register-cap builds of the quad form
     for env_id, n in (("DartWalker2d-v1", 16384), ("DartHalfCheetah-v1", 16384), ("DartHopper-v1", 65536), ("DartHopper-v1", 16384)):
         for pgs in ("", "30"):
