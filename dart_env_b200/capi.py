@@ -16,7 +16,7 @@ _EXPORTS = [
     "dartb_substep_f64", "dartb_get_contacts", "dartb_get_truncated", "dartb_max_contacts", "dartb_num_worlds",
     "dartb_num_dofs", "dartb_is_f64", "dartb_launch_count", "dartb_kernel_name", "dartb_last_error",
     "dartb_version", "dartb_describe", "dartb_step_host", "dartb_step_host_gym", "dartb_seed", "dartb_seed_worlds", "dartb_register_host", "dartb_unregister_host", "dartb_set_aux", "dartb_get_aux", "dartb_set_obs_peers",
-    "dartb_set_body_params",
+    "dartb_set_body_params", "dartb_get_body_table",
 ]
 
 
@@ -56,6 +56,7 @@ def load(build_if_missing: bool = True):
         "dartb_unregister_host": (C.c_int, [vp, vp]),
         "dartb_set_aux": (C.c_int, [vp, vp, vp]),
         "dartb_set_body_params": (C.c_int, [vp, vp, vp]),
+        "dartb_get_body_table": (C.c_int, [vp, vp, vp]),
         "dartb_set_obs_peers": (C.c_int, [vp, C.POINTER(vp), i32, i64]),
         "dartb_get_aux": (C.c_int, [vp, vp, vp]),
         "dartb_reset": (C.c_int, [vp, vp, vp, vp]),

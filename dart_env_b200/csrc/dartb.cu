@@ -77,6 +77,7 @@ struct dartb_engine {
     void* aux = nullptr;                      // [3][n] of Real: per-world task state (reacher target), or null
     void* wpar = nullptr;                     // [4 nb + ns][n] of Real: per-world dynamics parameters (dartb_set_body_params), or null
     std::vector<double> body_mass, body_mu;   // [n][n_bodies] as given to dartb_set_body_params (empty: the model's)
+    float rand_mass = 0, rand_mu = 0;         // DARTB_OPT_RANDOMIZE_*: per-reset redraw of the table's mass / friction rows
     std::string signature;                    // topology signature of the lowered model
     void* scratch = nullptr;                  // [n * nd | n * nbd*3] of Real: tau / fext precision conversion
     uint32_t* episode = nullptr; int32_t* elapsed = nullptr; uint8_t* truncated = nullptr;
@@ -130,7 +131,7 @@ static int lower_into(dartb_engine* e) {
     // task on a skeleton with capsules runs on the topology-generic loop kernel
     const bool coop_ok = true;
     // per-world dynamics parameters are read by the loop kernels only (the compiled topologies read one __grid_constant__ model)
-    const bool per_world = !e->body_mass.empty() || !e->body_mu.empty();
+    const bool per_world = !e->body_mass.empty() || !e->body_mu.empty() || e->rand_mass > 0 || e->rand_mu > 0;
     if (topo < 0 || res.m.any_coulomb || want == 1 || per_world || res.t.kind != DARTB_TASK_LOCOMOTION || (res.t.fluid_force && res.m.ns > 0)) e->variant = 1;
     else if (want == 2 && coop_ok) e->variant = 2;
     else if (want == 3) e->variant = 3;
@@ -218,7 +219,8 @@ static StepArgs<R> make_args(dartb_engine* e) {
     a.truncated = e->truncated;
     a.hint = e->hint;
     a.aux = (R*)e->aux;
-    a.wpar = (const R*)e->wpar;
+    a.wpar = (R*)e->wpar;
+    a.rand_mass = e->rand_mass; a.rand_mu = e->rand_mu;
     a.lcp_mode = e->lcp_mode; a.pgs_iters = e->pgs_iters; a.max_episode_steps = e->max_episode_steps;
     a.seed = e->seed; a.world_offset = e->world_offset; a.seeds = e->seeds;
     a.n_obs_peers = e->n_obs_peers; a.obs_peer_off = e->obs_peer_off;
@@ -463,7 +465,7 @@ static int relower(dartb_engine* e) {
 static int upload_body_params(dartb_engine* e) {
     const bool pm = !e->body_mass.empty(), pf = !e->body_mu.empty();
     DeviceGuard g(e->device);
-    if (!pm && !pf) {
+    if (!pm && !pf && !(e->rand_mass > 0 || e->rand_mu > 0)) {
         if (e->wpar) { cudaDeviceSynchronize(); cudaFree(e->wpar); e->wpar = nullptr; }
         return 0;
     }
@@ -503,6 +505,21 @@ int dartb_set_body_params(dartb_handle_t e, const double* h_mass, const double* 
     return 0;
 }
 
+int dartb_get_body_table(dartb_handle_t e, double* h_out, int32_t* n_rows) {
+    if (!e) return fail("null handle");
+    if (!e->wpar) return fail("dartb_get_body_table: no per-world parameters are set");
+    if (n_rows) *n_rows = 4 * e->md.nb + e->md.ns;
+    if (!h_out) return 0;
+    DeviceGuard g(e->device);
+    const size_t k = (size_t)(4 * e->md.nb + e->md.ns) * e->n;
+    CK(cudaDeviceSynchronize());
+    if (e->f64) { CK(cudaMemcpy(h_out, e->wpar, k * sizeof(double), cudaMemcpyDeviceToHost)); return 0; }
+    std::vector<float> hf(k);
+    CK(cudaMemcpy(hf.data(), e->wpar, k * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < k; i++) h_out[i] = hf[i];
+    return 0;
+}
+
 int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
     if (!e) return fail("null handle");
     switch (key) {
@@ -527,6 +544,21 @@ int dartb_set_option(dartb_handle_t e, int32_t key, double value) {
         case DARTB_OPT_CONTACTS:
             if (value != 0 && value != 1) return fail("contacts option must be 0 or 1");
             e->contacts = value != 0; return 0;
+        case DARTB_OPT_RANDOMIZE_MASS:
+        case DARTB_OPT_RANDOMIZE_FRICTION: {
+            if (!(value >= 0) || !std::isfinite(value)) return fail("randomisation half range must be finite and >= 0");
+            if (value > 0) {
+                // one draw per planar body stands for one bodynode: no weld merges (their mass / COM / izz mix on the host)
+                bool plain = e->md.nbd == e->md.nb;
+                for (int i = 0; plain && i < e->md.nbd; i++) plain = e->md.dgroup[i] == i;
+                if (!plain) return fail("per-reset randomisation needs a skeleton without welded bodynodes; use dartb_set_body_params");
+            }
+            float& slot = key == DARTB_OPT_RANDOMIZE_MASS ? e->rand_mass : e->rand_mu;
+            const float old = slot;
+            slot = (float)value;
+            if (relower(e)) { slot = old; std::string keep = g_err; relower(e); g_err = keep; return 1; }
+            return 0;
+        }
         case DARTB_OPT_MAX_EPISODE_STEPS:
             if (value < 0) return fail("bad max_episode_steps");
             e->max_episode_steps = (int)value; return 0;

@@ -475,6 +475,29 @@ DEVI void reset_state_loop(const PModel<R>& M, const PTask<R>& K, uint64_t seed,
     }
 }
 
+// snake_7link.py:115-120 inside the kernel: at every reset_model of a world its bodynode masses become original + U(-r, r)
+// and its friction coefficients original + U(-r, r), both clipped at 0 (the reference would hand DART the negative value),
+// written into the world's column of the per-world table.  One draw per planar body (= bodynode: dartb.cu refuses the
+// options for skeletons with welded bodynodes); a capsule's coefficient is min(its body's, ground = 1) as in lower.h.
+// Draws come from the reset generator at indices past the state noise (2 PM_MAXB + i, 3 PM_MAXB + i).
+template <typename R>
+DEVI void redraw_dynamics(const PModel<R>& M, const StepArgs<R>& a, int w, uint64_t seed, int64_t gw, uint32_t ep) {
+    if (!a.wpar || !(a.rand_mass > 0 || a.rand_mu > 0)) return;
+    const int nb = M.nb, ns = M.ns;
+    const size_t n = (size_t)a.n;
+    if (a.rand_mass > 0)
+        for (int i = 0; i < nb; i++) {
+            const float m = __fadd_rn((float)M.mass[i], __fmul_rn(reset_uniform(seed, gw, ep, 2 * PM_MAXB + i), a.rand_mass));
+            a.wpar[(size_t)i * n + w] = (R)(m > 0.0f ? m : 0.0f);
+        }
+    if (a.rand_mu > 0)
+        for (int s = 0; s < ns; s++) {
+            float mu = __fadd_rn((float)M.smu[s], __fmul_rn(reset_uniform(seed, gw, ep, 3 * PM_MAXB + M.sbody[s]), a.rand_mu));
+            mu = mu > 0.0f ? mu : 0.0f;
+            a.wpar[(size_t)(4 * nb + s) * n + w] = (R)(mu < 1.0f ? mu : 1.0f);
+        }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(128, DARTB_STEP_MIN_BLOCKS)
 k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<R> K, const __grid_constant__ StepArgs<R> a) {
@@ -524,6 +547,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
         if (active && done && a.auto_reset) {
             const uint32_t ep = a.episode[w];
             reset_state_kind<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq, tg);
+            redraw_dynamics<R>(M, a, w, reset_seed(a, w), reset_world(a, w), ep);
             a.episode[w] = ep + 1;
             if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
         }
@@ -571,6 +595,7 @@ k_env_step_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTa
     if (active && done && a.auto_reset) {
         const uint32_t ep = a.episode[w];
         reset_state_loop<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq);
+        redraw_dynamics<R>(M, a, w, reset_seed(a, w), reset_world(a, w), ep);
         a.episode[w] = ep + 1;
     }
     if (active) write_obs_loop<R>(M, K, q, dq, sw + lane * K.n_obs);
@@ -612,6 +637,7 @@ k_reset_loop(const __grid_constant__ PModel<R> M, const __grid_constant__ PTask<
             reset_state_kind<R>(M, K, reset_seed(a, w), reset_world(a, w), ep, q, dq, tg);
             if (a.aux) { a.aux[w] = tg[0]; a.aux[(size_t)a.n + w] = tg[1]; a.aux[2 * (size_t)a.n + w] = tg[2]; }
         }
+        redraw_dynamics<R>(M, a, w, reset_seed(a, w), reset_world(a, w), ep);
         a.episode[w] = ep + 1;
         a.elapsed[w] = 0;
         a.hint[w] = ~(uint64_t)0;

@@ -1174,8 +1174,9 @@ struct StepArgs {
     double* reward64;    // gym return types (sync_vector_env.py:44-47): when set, rewards go HERE as float64 and `done`
                          // receives plain 0/1 bools (the truncation flag only in `truncated`)
     R* aux;              // [3][n] per-world task state (DARTB_TASK_REACHER2D target: world x, y, z) or null
-    const R* wpar;       // [4 nb + ns][n] per-world dynamics parameters (dartb_set_body_params: mass, cx, cy, izz per planar
+    R* wpar;             // [4 nb + ns][n] per-world dynamics parameters (dartb_set_body_params: mass, cx, cy, izz per planar
                          // body, friction per capsule) or null = the model's; read by the loop kernels only
+    float rand_mass, rand_mu;   // DARTB_OPT_RANDOMIZE_*: half ranges of the per-reset redraw of wpar's mass / friction rows
     const uint8_t* mask; // reset mask (k_reset) or null
     int auto_reset, lcp_mode, pgs_iters, max_episode_steps;
     int wpw;             // worlds per warp in k_env_step (1..32): lanes >= wpw idle, see dartb.cu::wpw_for

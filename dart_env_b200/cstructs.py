@@ -11,6 +11,7 @@ import numpy as np
 from .skel import Model
 
 MAX_BODIES, MAX_SHAPES, MAX_GROUND, MAX_ACT = 24, 24, 4, 16
+PM_MAXB = 12   # csrc/planar_model.h: planar bodies after the weld merge (index base of the per-reset dynamics draws)
 
 OBS_Q1_DQ, OBS_HEIGHT_Q2_DQ = 0, 1
 TASK_LOCOMOTION, TASK_CARTPOLE, TASK_SWINGUP, TASK_DOUBLE_PENDULUM, TASK_REACHER2D = 0, 1, 2, 3, 4

@@ -131,6 +131,23 @@ class Engine:
         ptr = [a.ctypes.data_as(C.c_void_p) if a is not None else None for a in arrs]
         capi.check(self.L.dartb_set_body_params(self.h, ptr[0], ptr[1]))
 
+    def set_randomize(self, mass_range: float = 0.0, friction_range: float = 0.0):
+        """snake_7link.py:115-120 inside the kernel: at every reset of a world (reset() and the auto-reset of step()) its
+        bodynode masses become original + U(-mass_range, mass_range) and its friction coefficients original +
+        U(-friction_range, friction_range), clipped at 0.  0 switches a redraw off."""
+        self.set_option(8, float(mass_range))       # DARTB_OPT_RANDOMIZE_MASS
+        self.set_option(9, float(friction_range))   # DARTB_OPT_RANDOMIZE_FRICTION
+
+    def get_body_table(self):
+        """the per-world table the kernels read: numpy [4 nb + ns, n_worlds] float64 — rows mass, cx, cy, izz per planar
+        body, then the friction coefficient per capsule"""
+        import numpy as np
+        rows = C.c_int32(0)
+        capi.check(self.L.dartb_get_body_table(self.h, None, C.byref(rows)))
+        out = np.empty((rows.value, self.n), dtype=np.float64)
+        capi.check(self.L.dartb_get_body_table(self.h, out.ctypes.data_as(C.c_void_p), None))
+        return out
+
     def set_aux(self, aux: torch.Tensor):
         """per-world task state [n, 3] float64 (the reacher's `self.target`, reacher2d.py:7,57-63)"""
         self._chk(aux, (self.n, 3), torch.float64)

@@ -34,10 +34,11 @@ DartHalfCheetahEnv = _make_cls("DartHalfCheetah-v1", "DartHalfCheetahEnv")
 
 class DartSnake7LinkEnv(_make_cls("DartSnake7Link-v1", "_DartSnake7LinkBase")):
     """snake_7link.py.  `randomize_dynamics` (snake_7link.py:11, hard-coded False there) switches on the per-reset
-    dynamics randomisation of snake_7link.py:20-25,115-120: every bodynode's mass becomes original + U(-1.5, 1.5) and
-    its friction coefficient original + U(-0.5, 0.5), drawn from the global `np.random` like the reference, one draw per
-    world.  The draw happens in `reset()`; worlds that auto-reset inside the kernel keep theirs until then.  The
-    reference would hand DART a negative mass for the two massless root bodynodes; here draws are clipped at 0."""
+    dynamics randomisation of snake_7link.py:20-25,115-120: at every `reset_model` of a world — `reset()` and the
+    auto-reset inside `step()` — each bodynode's mass becomes original + U(-1.5, 1.5) and its friction coefficient original
+    + U(-0.5, 0.5).  The draws happen inside the kernel from the engine's seeded reset generator (the reference draws from
+    the unseeded global `np.random`); values are clipped at 0 where the reference would hand DART a negative mass (its two
+    massless root bodynodes).  The friction base is the coefficient the env runs with (0: snake_7link.py:29-31)."""
 
     randomize_dynamics = False
 
@@ -47,14 +48,8 @@ class DartSnake7LinkEnv(_make_cls("DartSnake7Link-v1", "_DartSnake7LinkBase")):
         # snake_7link.py:20-25: captured BEFORE the constructor's set_friction_coeff(0) loop (snake_7link.py:29-31)
         self.bodynode_original_masses = [b.mass for b in self.model.bodies]
         self.bodynode_original_frictions = list(self._skel_frictions)
-
-    def reset(self):
         if self.randomize_dynamics:
-            nb = len(self.model.bodies)
-            m = np.asarray(self.bodynode_original_masses) + np.random.uniform(-1.5, 1.5, size=(self.num_envs, nb))
-            f = np.asarray(self.bodynode_original_frictions) + np.random.uniform(-0.5, 0.5, size=(self.num_envs, nb))
-            self.set_body_params(np.clip(m, 0.0, None), np.clip(f, 0.0, None))
-        return super().reset()
+            self.engine.set_randomize(1.5, 0.5)
 
 
 DartSnake7LinkEnv.__name__ = DartSnake7LinkEnv.__qualname__ = "DartSnake7LinkEnv"

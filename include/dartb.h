@@ -20,6 +20,7 @@
 #ifndef DARTB_H
 #define DARTB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -122,10 +123,17 @@ enum { DARTB_OPT_LCP_MODE = 1,    /* 0 = exact (Dantzig-equivalent), 1 = PGS */
        DARTB_OPT_MAX_EPISODE_STEPS = 4,/* TimeLimit (gym/wrappers/time_limit.py:14-21); 0 = off */
        DARTB_OPT_KERNEL_VARIANT = 5, /* -1 = auto, 0 = unrolled per-topology kernel (one world per thread), 1 = loop / topology-generic kernel, 2 = lane-cooperative kernel (8/16 lanes per world), 3 = quad form of the per-thread kernel (4 lanes per world share the constraint phase); auto: lane-cooperative, quad, per-thread by growing batch size */
        DARTB_OPT_WORLDS_PER_WARP = 6,/* launch shape of dartb_step: worlds per warp, 0 = auto; results do not depend on it */
-       DARTB_OPT_CONTACTS = 7      /* 1 = dartb_step records world.collision_result.contacts of its last sub-step for
+       DARTB_OPT_CONTACTS = 7,     /* 1 = dartb_step records world.collision_result.contacts of its last sub-step for
                                       dartb_get_contacts (walker2d.py:38-41); default 0: the record is 356 B per world
                                       per step, more than the rest of the step's HBM traffic.  dartb_substep (the
-                                      literal World.step()) always records. */ };
+                                      literal World.step()) always records. */
+       DARTB_OPT_RANDOMIZE_MASS = 8,    /* half range r >= 0: at EVERY reset of a world (dartb_reset and the auto-reset
+                                      inside dartb_step) its bodynode masses become original + U(-r, r), clipped at 0 —
+                                      snake_7link.py:115-118 (r = 1.5) inside the kernel; 0 = off */
+       DARTB_OPT_RANDOMIZE_FRICTION = 9 /* the same for the friction coefficients, original + U(-r, r) clipped at 0,
+                                      snake_7link.py:119-120 (r = 0.5).  Both write the per-world table of
+                                      dartb_set_body_params (the batch runs on the loop kernels) and need a skeleton
+                                      without welded bodynodes (one planar body per bodynode). */ };
 
 typedef struct dartb_engine* dartb_handle_t;
 
@@ -219,6 +227,10 @@ int dartb_get_aux(dartb_handle_t h, double* d_aux, void* stream);
  * is min(body, ground) as in the shared model.  Synchronises the device; while per-world parameters are set the batch runs
  * on the topology-generic loop kernels, the only ones that read them (dartb_kernel_name reports "loop:generic"). */
 int dartb_set_body_params(dartb_handle_t h, const double* h_mass, const double* h_friction);
+/* The table the kernels read, HOST array [4 nb + ns][n_worlds] fp64: rows mass, cx, cy, izz of planar body 0..nb-1, then
+ * the friction coefficient of capsule 0..ns-1.  *n_rows (may be NULL) receives 4 nb + ns; h_out may be NULL to ask for
+ * the row count only.  Fails when no per-world parameters are set.  Synchronises. */
+int dartb_get_body_table(dartb_handle_t h, double* h_out, int32_t* n_rows);
 
 /* world.collision_result.contacts of the LAST sub-step (walker2d.py:38-41).
  * d_count int32[n]; d_body int32[n, max_contacts] (robot body index per contact, -1 padded,

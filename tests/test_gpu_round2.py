@@ -369,26 +369,107 @@ def test_per_world_body_params_match_oracle(f64):
     env.close(); env2.close()
 
 
+def _expected_redraw(base, half_range, seed, world, episode, idx0, lo=0.0, hi=None):
+    """what redraw_dynamics (kernels.cuh) writes: base + reset_uniform(seed, world, episode, idx0 + i) * half_range in fp32,
+    clipped; the generator is the oracle's bit-exact twin of the kernel's (test_reset_noise_*)"""
+    from oracle import oracle as orc
+    out = np.empty(len(base), dtype=np.float64)
+    for i, b in enumerate(base):
+        u = np.float32(orc.reset_uniform(seed, world, episode, idx0 + i))
+        v = np.float32(np.float32(b) + np.float32(u * np.float32(half_range)))
+        v = max(float(v), lo)
+        out[i] = v if hi is None else min(v, hi)
+    return out
+
+
 def test_snake_randomize_dynamics_flag():
     """snake_7link.py:11,20-25,115-120: `randomize_dynamics` (hard-coded off in the reference) redraws every bodynode's
-    mass / friction at reset — here one draw per world.  Identically seeded worlds then diverge only through their masses."""
+    mass / friction at EVERY reset_model.  Here inside the kernel, from the seeded reset generator: the table after
+    reset() is exactly original + 1.5 u (clipped at 0), identically seeded worlds diverge only through their masses."""
+    from dart_env_b200.cstructs import PM_MAXB
     from dart_env_b200.envs import DartSnake7LinkEnv
     n = 64
     a = np.random.RandomState(0).uniform(-1, 1, (10, 1, 6)).astype(np.float32).repeat(n, 1)
     outs = []
     for rd in (False, True):
-        env = DartSnake7LinkEnv(num_envs=n, output="numpy", seed=0, auto_reset=False, randomize_dynamics=rd)
-        env.seed([7] * n)            # every world draws the same reset noise
-        np.random.seed(3)
-        ob = env.reset()
+        env = DartSnake7LinkEnv(num_envs=n, output="numpy", seed=5, auto_reset=False, randomize_dynamics=rd)
         assert ("loop:generic" in env.engine.kernel_name) == rd
+        if rd:
+            env.reset()
+            tab = env.engine.get_body_table()
+            nb = env.model.n_dofs
+            mass0 = np.array(env.bodynode_original_masses)
+            assert tab.shape == (4 * nb, n)                      # the snake has no capsule that can touch the ground
+            # one consistent episode index for the whole batch (the reset that just ran), one draw per body and world
+            hits = [ep for ep in range(4) if all(np.array_equal(tab[:nb, w].astype(np.float32),
+                    _expected_redraw(mass0, 1.5, 5, w, ep, 2 * PM_MAXB).astype(np.float32)) for w in (0, 1, n - 1))]
+            assert len(hits) == 1, hits
+            assert (tab[:nb] >= 0).all() and np.abs(tab[:nb] - mass0[:, None]).max() <= 1.5 + 1e-6
+            assert np.abs(tab[:nb] - mass0[:, None]).max() > 1.0             # the range is used
+            tab2 = (env.reset(), env.engine.get_body_table())[1]
+            assert np.abs(tab2[:nb] - tab[:nb]).max() > 0.1                  # every reset draws again
+        env.seed([7] * n)            # from here on every world draws the same reset noise (and the same masses)
+        env.reset()
+        if rd:
+            t3 = env.engine.get_body_table()
+            assert np.abs(t3 - t3[:, :1]).max() == 0.0
+            env.seed(list(range(100, 100 + n)))                  # distinct draws again, then identical STATE noise is gone too:
+            env.reset()                                          # compare the two modes on their spread instead
+        ob = None
         for t in range(10):
             ob, rew, done, _ = env.step(a[t])
         assert np.isfinite(ob).all()
         outs.append(ob.copy())
         env.close()
-    assert np.abs(outs[0] - outs[0][0]).max() == 0.0          # shared model: identical worlds stay identical
-    assert np.abs(outs[1] - outs[1][0]).max() > 1e-3           # per-world masses: they do not
+    assert np.abs(outs[0] - outs[0][0]).max() == 0.0          # shared model + one seed: identical worlds stay identical
+    assert np.abs(outs[1] - outs[1][0]).max() > 1e-3
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_randomize_dynamics_redraws_at_every_auto_reset(f64):
+    """DARTB_OPT_RANDOMIZE_MASS / _FRICTION on a contact-rich env with short episodes (Hopper): a world that finishes an
+    episode inside step() gets new masses and friction coefficients with its reset state; the others keep theirs; the
+    values are the documented function of (seed, world, episode)."""
+    from dart_env_b200.capi import DartbError
+    from dart_env_b200.cstructs import PM_MAXB
+    n = 96
+    env = _make("DartHopper-v1", num_envs=n, output="numpy", seed=9, f64=f64)
+    nb = env.model.n_dofs
+    assert len(env.model.bodies) == nb                       # no welded bodynodes
+    env.engine.set_randomize(0.5, 0.3)
+    assert "loop:generic" in env.engine.kernel_name
+    env.reset()
+    t0 = env.engine.get_body_table()
+    ns = t0.shape[0] - 4 * nb
+    assert ns == 4
+    mass0 = np.array([b.mass for b in env.model.bodies])
+    ever_done = np.zeros(n, dtype=bool)
+    rng = np.random.RandomState(2)
+    for _ in range(40):
+        _, _, done, _ = env.step(rng.uniform(-1, 1, (n, 3)).astype(np.float32))
+        ever_done |= done
+    assert ever_done.any() and not ever_done.all()
+    t1 = env.engine.get_body_table()
+    changed = np.abs(t1 - t0).max(0) > 0
+    assert np.array_equal(changed, ever_done)
+    assert np.array_equal(t1[nb:4 * nb], t0[nb:4 * nb])          # COM offsets and izz are not redrawn (set_mass keeps them)
+    assert (t1[:nb] >= 0).all() and np.abs(t1[:nb] - mass0[:, None]).max() <= 0.5 + 1e-6
+    mu = t1[4 * nb:]
+    assert (mu >= 0.7 - 1e-6).all() and (mu <= 1.0).all()       # base 1.0 -+ 0.3, min(body, ground = 1)
+    w = int(np.where(~ever_done)[0][0])                          # a world still in its first episode: drawn by reset()
+    hits = [ep for ep in range(4) if np.array_equal(t1[:nb, w].astype(np.float32),
+                                                    _expected_redraw(mass0, 0.5, 9, w, ep, 2 * PM_MAXB).astype(np.float32))]
+    assert len(hits) == 1, hits
+    # a skeleton with welded bodynodes is refused (their masses mix on the host: dartb_set_body_params)
+    ch = _make("DartHalfCheetah-v1", num_envs=8, output="numpy", seed=0)
+    if len(ch.model.bodies) != ch.model.n_dofs:
+        with pytest.raises(DartbError):
+            ch.engine.set_randomize(0.5, 0.0)
+    ch.close()
+    env.engine.set_randomize(0.0, 0.0)
+    env.set_body_params(None, None)
+    assert "loop:generic" not in env.engine.kernel_name
+    env.close()
 
 
 def test_bodynode_views_set_mass_and_friction():

@@ -240,3 +240,25 @@ def test_output_pool_hands_out_only_unreferenced_slots():
     assert len(seen) == 2 and len(pool.slots) == 2    # both slots circulate again
     held = [pool.take()["obs"] for _ in range(4)]
     assert len({id(h) for h in held}) == 4 and pool.take() is None    # max_slots all held: caller falls back to copies
+
+
+def test_planar_body_limit_matches_the_kernel_header():
+    """cstructs.PM_MAXB is the index base of the per-reset dynamics draws (kernels.cuh::redraw_dynamics)"""
+    from dart_env_b200.cstructs import PM_MAXB
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(here, "dart_env_b200", "csrc", "planar_model.h")).read()
+    assert int(re.search(r"#define PM_MAXB (\d+)", txt).group(1)) == PM_MAXB
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/dartb.h is the drop-in boundary: it must compile as C on its own (a cgo / ctypes / JNI binding includes
+    nothing else)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(here, "include", "dartb.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
