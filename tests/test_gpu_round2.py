@@ -445,9 +445,11 @@ def test_randomize_dynamics_redraws_at_every_auto_reset(f64):
     mass0 = np.array([b.mass for b in env.model.bodies])
     ever_done = np.zeros(n, dtype=bool)
     rng = np.random.RandomState(2)
-    for _ in range(40):
+    for _ in range(40):     # (random actions end a Hopper episode after ~4 steps: stop while some worlds are still in their first)
         _, _, done, _ = env.step(rng.uniform(-1, 1, (n, 3)).astype(np.float32))
         ever_done |= done
+        if ever_done.sum() >= n // 4:
+            break
     assert ever_done.any() and not ever_done.all()
     t1 = env.engine.get_body_table()
     changed = np.abs(t1 - t0).max(0) > 0
