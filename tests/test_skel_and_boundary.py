@@ -262,3 +262,14 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(here, "include", "dartb.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_integration_doc_lists_every_export():
+    """INTEGRATION.md maps each C-ABI entry point to the reference call it replaces: none may be missing"""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(here, "include", "dartb.h")).read()
+    doc = open(os.path.join(here, "INTEGRATION.md")).read()
+    names = set(re.findall(r"^(?:int|int32_t|int64_t|const char\*)\s+(dartb_[a-z0-9_]+)\(", hdr, flags=re.M))
+    assert len(names) > 30
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
