@@ -117,6 +117,38 @@ def test_aba_equals_autodiff_lagrangian_locomotion(models, env_id):
     assert worst < 1e-9, worst
 
 
+def test_set_mass_equals_lagrangian_with_that_mass_and_the_original_moment(models):
+    """bodynode.set_mass (snake_7link.py:117; DART 6 Inertia::setMass: the mass changes, the moment of inertia about the COM
+    stays): the oracle world after set_mass must move like the autodiff Lagrangian of a skeleton with those masses and
+    the ORIGINAL moments — the semantics the per-world tables of dartb_set_body_params are lowered with."""
+    import copy
+    model = models["DartWalker2d-v1"]
+    rng = np.random.default_rng(4)
+    changed = copy.deepcopy(model)
+    w = orc.OracleWorld(model)
+    for i, b in enumerate(changed.bodies):
+        if b.mass > 0:
+            b.mass = float(b.mass + rng.uniform(-1.5, 1.5))
+            w.set_mass(i, b.mass)
+    nd = model.n_dofs
+    q = np.array(model.q_init(), dtype=float) + rng.uniform(-0.4, 0.4, nd)
+    q[1] += 2.0
+    for d, bi in enumerate(model.dof_bodies()):
+        b = model.bodies[bi]
+        if b.limit_enforced:
+            q[d] = np.clip(q[d], b.q_lo + 0.05, b.q_hi - 0.05)
+    dq, tau = rng.uniform(-3, 3, nd), rng.uniform(-20, 20, nd)
+    w.set_state(q, dq)
+    w.set_forces(tau)
+    ddq_lag, M = _lagrange_ddq(changed, q, dq, tau)
+    assert np.allclose(M, w.mass_matrix(), rtol=1e-9, atol=1e-10)
+    assert np.abs(w.forward_dynamics() - ddq_lag).max() / (1 + np.abs(ddq_lag).max()) < 1e-9
+    # and it is not the original skeleton's motion
+    w0 = orc.OracleWorld(model)
+    w0.set_state(q, dq); w0.set_forces(tau)
+    assert np.abs(w0.forward_dynamics() - ddq_lag).max() > 1e-2
+
+
 # ------------------------------------------------------------------ 2. momentum balance of the contact step
 def _total_momentum(w, model):
     P = np.zeros(3)
