@@ -4,6 +4,7 @@ Each (topology, precision) instantiation of the kernels is its own translation u
 compiled with -DINST_*), built in parallel, then linked with the host API (dartb.cu)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,9 +32,27 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = SO + ".srchash"   # sha256 of the sources the library was built from (travels with the .so)
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read() + b"\0")
+    h.update(" ".join(ARCH + COMMON).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
+    """The library is stale when its sources changed.  Decided by CONTENT when the stamp written at build time is there:
+    a copy of the tree (the snapshot a GPU box receives) need not preserve modification times, and a spurious rebuild there
+    costs minutes inside the first test that loads the library.  Without a stamp: by modification time."""
     if not os.path.exists(SO):
         return True
+    if os.path.exists(STAMP):
+        with open(STAMP) as f:
+            return f.read().strip() != source_hash()
     t = os.path.getmtime(SO)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
@@ -75,6 +94,11 @@ def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
     log = _run([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", SO] + [j[0] for j in jobs_all], verbose)
     if verbose:
         sys.stderr.write("".join(logs) + log)
+    if not only:   # (a partial developer rebuild leaves the other objects as they were: keep the previous verdict)
+        with open(STAMP, "w") as f:
+            f.write(source_hash() + "\n")
+    elif os.path.exists(STAMP):
+        os.remove(STAMP)
     return SO
 
 

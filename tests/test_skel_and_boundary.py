@@ -273,3 +273,21 @@ def test_integration_doc_lists_every_export():
     assert len(names) > 30
     missing = sorted(n for n in names if n not in doc)
     assert not missing, missing
+
+
+def test_library_staleness_is_decided_by_content(tmp_path, monkeypatch):
+    """build.is_stale(): a copy of the tree that does not preserve modification times (the GPU box's snapshot) must not
+    trigger a rebuild; a changed source must."""
+    from dart_env_b200 import build as b
+    if not os.path.exists(b.STAMP):
+        pytest.skip("library built without a stamp")
+    assert not b.is_stale()
+    src = os.path.join(b.CSRC, "lower.h")
+    st = os.stat(src)
+    try:
+        os.utime(src)                       # newer than the library, same content
+        assert not b.is_stale()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    monkeypatch.setattr(b, "source_hash", lambda: "0" * 64)
+    assert b.is_stale()
