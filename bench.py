@@ -27,7 +27,10 @@ working set is far smaller than L2; max over ranks.  `value` is device-resident 
 actions from and writes obs / float64 rewards / bool dones to page-locked host memory, one launch
 + one sync per step) and is the headline against `--impl reference`, which times the CPU
 restatement of the reference path (oracle/, "port": pydart2/DART are not installable here) on all
-host threads for at least 8 s of CPU work regardless of --steps.
+host threads for at least 10 s of CPU work regardless of --steps.  `e2e.value` is the MEAN over
+every call (wall clock, L2 flushed between calls, cyclic GC off inside the loop like `timeit`, the
+nvidia-smi clocks poll stopped once the device-timed regions end); `e2e.us_per_call_rank0` adds the
+p50 / p99 / max of the same calls.
 """
 import argparse
 import gc
