@@ -340,3 +340,28 @@ def test_per_world_body_params_equal_oracle_set_mass_set_friction(models, env_id
     q3, dq3, *_ = emu.substep_body_params(m, SPECS[env_id].task, g["sub_q"][idx], g["sub_dq"][idx], g["sub_tau"][idx],
                                           mass=np.tile(mass0, (len(idx), 1)), friction=None, f64=True)
     assert np.allclose(dq3, dq0, rtol=1e-12, atol=1e-12)
+
+
+def test_branch_free_sincos_accuracy():
+    """Num<float>::sincos_ (Cody-Waite reduction by pi/2 + minimax polynomials, no branches) against double precision:
+    <= 2 ulp like libm's sincosf over the range joint angles can reach, exact identities at the special points."""
+    import ctypes as C
+    L = emu.lib()
+    rng = np.random.RandomState(0)
+    fp = C.POINTER(C.c_float)
+    for R in (3.2, 100.0, 1e4, 1e5):
+        x = rng.uniform(-R, R, 400000).astype(np.float32)
+        s, c = np.empty_like(x), np.empty_like(x)
+        L.emu_sincos(len(x), x.ctypes.data_as(fp), s.ctypes.data_as(fp), c.ctypes.data_as(fp))
+        xs = x.astype(np.float64)
+        rs, rc = np.sin(xs), np.cos(xs)
+        ulp_s = np.abs(s - rs) / np.spacing(np.abs(rs).astype(np.float32))
+        ulp_c = np.abs(c - rc) / np.spacing(np.abs(rc).astype(np.float32))
+        assert ulp_s.max() <= 2.0 and ulp_c.max() <= 2.0, (R, ulp_s.max(), ulp_c.max())
+        assert np.abs(s - rs).max() < 1.2e-7 and np.abs(c - rc).max() < 1.2e-7
+        assert np.abs(s.astype(np.float64) ** 2 + c.astype(np.float64) ** 2 - 1).max() < 4e-7
+    x = np.array([0.0, -0.0, 1e-30, -1e-30, np.pi / 2, -np.pi / 2, np.pi, 2 * np.pi, 1e-4], dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    L.emu_sincos(len(x), x.ctypes.data_as(fp), s.ctypes.data_as(fp), c.ctypes.data_as(fp))
+    assert s[0] == 0 and c[0] == 1 and s[1] == 0 and c[1] == 1 and s[2] == x[2] and s[3] == x[3] and c[2] == 1
+    assert np.allclose(s, np.sin(x.astype(np.float64)), atol=1e-7) and np.allclose(c, np.cos(x.astype(np.float64)), atol=1e-7)

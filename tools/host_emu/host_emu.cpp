@@ -134,6 +134,11 @@ extern "C" void emu_counters(long* out, int reset) { for (int i = 0; i < 8; i++)
 
 static std::string g_err;
 
+// Num<float>::sincos_ / Num<double>::sincos_ of the kernel source, element-wise (the branch-free fp32 form's accuracy test)
+extern "C" void emu_sincos(int n, const float* x, float* s, float* c) {
+    for (int i = 0; i < n; i++) Num<float>::sincos_(x[i], &s[i], &c[i]);
+}
+
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
 
 // the loop kernel's sub-step with per-world bodynode masses / friction coefficients ([n][n_bodies], either may be null):
