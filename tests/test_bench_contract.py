@@ -72,3 +72,18 @@ def test_algorithmic_bytes_follow_survey_8d(bench):
     # 4 * (2 nd + nact + 2 nd + nobs + 1) + 1 bytes per env step; Hopper nd 6, nact 3, nobs 11 -> 157
     assert bench.algo_bytes(6, 3, 11) == 157
     assert bench.algo_bytes(9, 6, 17) == 241
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm like the GPU arm (torchrun, one process per GPU); rank 0 alone runs and
+    prints the line, the other ranks exit 0 without work."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=400)
+    assert out.returncode == 0, out.stderr[-600:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
